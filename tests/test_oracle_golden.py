@@ -1,0 +1,132 @@
+"""Pin the oracle (oracle/u1_oracle.py) against the real reference's outputs
+(tests/golden/*.npz, made by tools/gen_golden.py), the reference's own golden log
+tests/test.out, and the dense-Jacobian self check (field_trans_opt.py:385-390)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import u1_oracle as O
+
+T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("tag", ["L6_b1p5", "L16_b2", "L64_b6"])
+def test_plain_matches_reference(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f"plain_{tag}.npz"))
+    th, pi = T(z["theta"]), T(z["pi"])
+    beta, n, dt = float(z["beta"]), int(z["n_steps"]), float(z["dt"])
+    assert rel(O.plaq_from_field(th), z["plaq_field"]) < 1e-15
+    assert rel(O.regularize(th * 3.7), z["regularized"]) == 0.0
+    assert abs(O.action(th, beta).item() - float(z["action"])) <= 1e-13 * abs(float(z["action"]))
+    assert rel(O.force_autograd(th, beta), z["force"]) < 1e-15
+    assert rel(O.force_analytic(th, beta), z["force"]) < 1e-14
+    h = O.PlainHMCOracle(int(z["L"]), beta, n, dt)
+    th2, pi2 = h.leapfrog(th, pi)
+    assert rel(th2, z["theta_out"]) < 1e-13 and rel(pi2, z["pi_out"]) < 1e-13
+    assert abs(O.plaq_mean(th).item() - float(z["plaq"])) < 1e-15
+    assert O.topo_charge(th).item() == float(z["topo"])
+    _, _, _, dH = h.metropolis_step(th[None], pi[None], torch.tensor([0.5], dtype=torch.float64))
+    assert abs(dH.item() - float(z["dH"])) < 1e-10 * max(1.0, abs(float(z["dH"])))
+
+
+@pytest.mark.parametrize("tag,wfile", [
+    ("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L8", "weights_simple_beta6.0.npz"),
+    ("rnet1_L8", "weights_rnet1_beta6.0.npz"), ("rnet3_L16_b3", "weights_rnet3_beta3.0.npz"),
+    ("rnet3_L32_b3", "weights_rnet3_beta3.0.npz"), ("rnet3_L64_b6", "weights_rnet3_beta6.0.npz"),
+    ("simple_L64_b6", "weights_simple_beta6.0.npz"), ("rnet1_L64_b6", "weights_rnet1_beta6.0.npz"),
+])
+def test_ft_matches_reference(golden_dir, tag, wfile):
+    z = np.load(os.path.join(golden_dir, f"ft_{tag}.npz"))
+    arch, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    assert arch == str(z["arch"])
+    L, beta = int(z["L"]), float(z["beta"])
+    ft = O.FieldTransformationOracle(L, nets)
+    th = T(z["theta"])[None]
+    assert rel(ft.ft_phase(th, 0)[0], z["phase0"]) < 1e-13
+    assert rel(ft.ft_phase(th, 5)[0], z["phase5"]) < 1e-13
+    X, _, _ = ft.features(th, 3)
+    K0, K1 = ft.nets[3](X)
+    assert rel(K0[0], z["K0_3"]) < 1e-13 and rel(K1[0], z["K1_3"]) < 1e-13
+    ori, ld = ft.forward_and_logdet(th)
+    assert rel(ori[0], z["theta_ori"]) < 1e-13
+    assert abs(ld.item() - float(z["logdet"])) < 1e-13 * abs(float(z["logdet"]))
+    assert rel(ft.forward(th)[0], z["theta_ori"]) < 1e-13
+    S = ft.new_action(th, beta)
+    assert abs(S.item() - float(z["new_action"])) < 1e-13 * abs(float(z["new_action"]))
+    assert rel(ft.new_force(th, beta)[0], z["new_force"]) < 1e-12
+    if "logdet_dense" in z.files:       # if_check_jac path, field_trans_opt.py:385-390
+        assert abs(ld.item() - float(z["logdet_dense"])) < 1e-12 * abs(ld.item())
+        assert abs(ft.logdet_dense_autograd(th[0]).item() - ld.item()) < 1e-12 * abs(ld.item())
+    if L <= 16:                         # short FT leapfrog (5 steps) incl. dH
+        h = O.FTHMCOracle(ft, beta, int(z["n_steps"]), float(z["dt"]))
+        th2, pi2 = h.leapfrog(th, T(z["pi"])[None])
+        assert rel(th2[0], z["theta_out"]) < 1e-11 and rel(pi2[0], z["pi_out"]) < 1e-11
+
+
+def test_ft_phase_loop_spec(golden_dir):
+    """Explicit index loops against the roll-based restatement."""
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, "weights_rnet1_beta6.0.npz"))
+    L = 6
+    ft = O.FieldTransformationOracle(L, nets)
+    g = torch.Generator().manual_seed(7)
+    th = torch.randn(1, 2, L, L, generator=g, dtype=torch.float64)
+    for k in range(8):
+        X, _, _ = ft.features(th, k)
+        K0, K1 = ft.nets[k](X)
+        d = O.ft_phase_loops(th[0].numpy(), K0[0].numpy(), K1[0].numpy(), k)
+        assert np.max(np.abs(d - ft.ft_phase(th, k)[0].numpy())) < 5e-16
+        # triangular Jacobian premise: K of subset k does not depend on subset-k links
+        th2 = th.clone(); th2[0][ft.fm[k]] += 0.37
+        X2, _, _ = ft.features(th2, k)
+        assert torch.equal(X, X2) or float((X - X2).abs().max()) < 1e-15
+
+
+def test_masks_partition():
+    L = 8
+    tot = sum(O.field_mask(k, L).to(torch.int32) for k in range(8))
+    assert torch.all(tot == 1)
+
+
+def test_replay_reference_golden_log(golden_dir):
+    """tests/test.out (tests/hmc_2DU1.py): seed 1984, randn_like then rand([]) per trajectory."""
+    with open(os.path.join(golden_dir, "test_out_head.json")) as f:
+        G = json.load(f)
+    L, beta, n = G["L"], G["beta"], G["nstep"]
+    dt = G["tau"] / n
+    torch.manual_seed(G["seed"])
+    x = torch.zeros(2, L, L, dtype=torch.float64)
+    h = O.PlainHMCOracle(L, beta, n, dt)
+    for row in G["rows"][:10]:
+        p = torch.randn_like(x)
+        u = torch.rand([], dtype=torch.float64)
+        x1, acc, _, dH = h.metropolis_step(x[None], p[None], u[None])
+        x = x1[0]
+        assert bool(acc.item()) == row["accept"]
+        assert abs(dH.item() - row["dH"]) <= 2e-7 * max(1.0, abs(row["dH"])), (row, dH.item())
+        assert abs(O.plaq_mean(x).item() - row["plaq"]) < 5e-8
+        assert O.topo_charge(x).item() == row["topo"]
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for c, k, want in kat:
+        got = O.philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0]
+        assert [int(v) for v in got] == want
+    p = O.philox_momenta(1331, 5, 17, 16)
+    assert p.shape == (2, 16, 16) and abs(p.mean()) < 0.2 and 0.8 < p.std() < 1.2
+    assert 0.0 < O.philox_accept_uniform(1331, 5, 17) < 1.0
