@@ -1,0 +1,843 @@
+// Plain 2D U(1) HMC on sm_100a: streaming (one fused drift+force+kick kernel per leapfrog
+// step, HBM-bound, any L / slabs) and SM-resident (whole trajectory in registers, one CTA per
+// chain, L in {8,16,32,64}) paths behind the C ABI of include/u1hmc.h.
+//
+// Reference semantics: 2d_u1_cluster/hmc_u1.py:56-97,219-225 and utils.py:118-196.
+#include "u1_common.cuh"
+
+namespace u1 {
+
+thread_local long long g_launches = 0;
+
+// ---------------------------------------------------------------------------------------
+// Elementwise primitives
+// ---------------------------------------------------------------------------------------
+__global__ void k_plaquette(const double* __restrict__ th, double* __restrict__ out, int B, int L) {
+    const long long n = (long long)B * L * L;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
+         s += (long long)gridDim.x * blockDim.x) {
+        const int V = L * L;
+        const int b = (int)(s / V), r = (int)(s - (long long)b * V);
+        const int x = r / L, y = r - x * L;
+        const double* t0 = th + (size_t)b * 2 * V;
+        const double* t1 = t0 + V;
+        const int yp = wrapi(y + 1, L), xp = wrapi(x + 1, L);
+        out[s] = t0[x * L + y] - t1[x * L + y] - t0[x * L + yp] + t1[xp * L + y];
+    }
+}
+
+__global__ void k_rectangle(const double* __restrict__ th, double* __restrict__ out, int B, int L) {
+    const long long n = (long long)B * L * L;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
+         s += (long long)gridDim.x * blockDim.x) {
+        const int V = L * L;
+        const int b = (int)(s / V), r = (int)(s - (long long)b * V);
+        const int x = r / L, y = r - x * L;
+        const double* t0 = th + (size_t)b * 2 * V;
+        const double* t1 = t0 + V;
+        const int y1 = wrapi(y + 1, L), y2 = wrapi(y + 2, L), x1 = wrapi(x + 1, L), x2 = wrapi(x + 2, L);
+        // utils.py:137-139, same term order as the reference
+        const double r0 = t0[x * L + y] + t0[x1 * L + y] + t1[x2 * L + y] - t0[x1 * L + y1] -
+                          t0[x * L + y1] - t1[x * L + y];
+        const double r1 = t0[x * L + y] + t1[x1 * L + y] + t1[x1 * L + y1] - t0[x * L + y2] -
+                          t1[x * L + y1] - t1[x * L + y];
+        out[(size_t)b * 2 * V + r] = r0;
+        out[(size_t)b * 2 * V + V + r] = r1;
+    }
+}
+
+__global__ void k_regularize(const double* __restrict__ in, double* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = wrap_pi(in[i]);
+}
+
+// theta_out = regularize(theta + a*pi): last half drift of hmc_u1.py:78-79.
+__global__ void k_final_drift(const double* __restrict__ th, const double* __restrict__ pi,
+                              double* __restrict__ out, double a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = wrap_pi(fma(a, pi[i], th[i]));
+}
+
+__global__ void k_momenta(double* __restrict__ pi, uint64_t seed, uint64_t chain0, uint64_t traj,
+                          int B, int L) {
+    const int V = L * L;
+    const long long n = (long long)B * V;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
+         s += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(s / V), site = (int)(s - (long long)b * V);
+        double n0, n1;
+        philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, n0, n1);
+        pi[(size_t)b * 2 * V + site] = n0;
+        pi[(size_t)b * 2 * V + V + site] = n1;
+    }
+}
+
+// hmc_u1.py:65-69 closed form.  Not on the trajectory path (the step kernel fuses it).
+__global__ void k_force(const double* __restrict__ th, double* __restrict__ F, int B, int L, double beta) {
+    const long long n = (long long)B * L * L;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
+         s += (long long)gridDim.x * blockDim.x) {
+        const int V = L * L;
+        const int b = (int)(s / V), r = (int)(s - (long long)b * V);
+        const int x = r / L, y = r - x * L;
+        const double* t0 = th + (size_t)b * 2 * V;
+        const double* t1 = t0 + V;
+        const int yp = wrapi(y + 1, L), xp = wrapi(x + 1, L), ym = wrapi(y - 1, L), xm = wrapi(x - 1, L);
+        const double p = t0[x * L + y] - t1[x * L + y] - t0[x * L + yp] + t1[xp * L + y];
+        const double pl = t0[x * L + ym] - t1[x * L + ym] - t0[x * L + y] + t1[xp * L + ym];   // P(x,y-1)
+        const double pu = t0[xm * L + y] - t1[xm * L + y] - t0[xm * L + yp] + t1[x * L + y];   // P(x-1,y)
+        const double sp = sin(wrap_pi(p));
+        F[(size_t)b * 2 * V + r] = beta * (sp - sin(wrap_pi(pl)));
+        F[(size_t)b * 2 * V + V + r] = beta * (-sp + sin(wrap_pi(pu)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Streaming fused leapfrog step:  theta' = theta + drift*pi ;  pi' = pi - kick*F(theta')
+// One CTA = TR x TC sites staged in shared memory with a one-site periodic halo.
+// Algorithmic HBM traffic: read theta0,theta1,pi0,pi1 + write the same = 64 B / site-update.
+// ---------------------------------------------------------------------------------------
+struct StepArgs {
+    const double* th;  const double* pi;
+    double* tho;       double* pio;
+    const double* th_up; const double* pi_up;   // slab halos (row x=-1), [2][L]
+    const double* th_dn; const double* pi_dn;   // slab halos (row x=Lx), [2][L]
+    int Lx, L, TR, TC, tiles_y;
+    double beta, drift, kick;
+};
+
+constexpr int kStepThreads = 256;
+constexpr int kStepMaxUnits = 2;   // double2 units per thread (tile <= 1024 sites)
+
+template <bool SLAB>
+__global__ void __launch_bounds__(kStepThreads) k_leapfrog_step(StepArgs a) {
+    extern __shared__ double sm[];
+    const int TR = a.TR, TC = a.TC, L = a.L, Lx = a.Lx;
+    const int W = TC + 2;                       // padded row width of the theta' tiles
+    double* t0 = sm;                            // (TR+2) x (TC+2), origin at (-1,-1)
+    double* t1 = t0 + (TR + 2) * W;
+    double* sp = t1 + (TR + 2) * W;             // (TR+1) x (TC+1), origin at (-1,-1)
+    const int WS = TC + 1;
+
+    const int tile = blockIdx.x;
+    const int x0 = (tile / a.tiles_y) * TR, y0 = (tile % a.tiles_y) * TC;
+    const size_t V = (size_t)Lx * L;
+    const size_t base = (size_t)blockIdx.y * 2 * V;
+    const double* g0 = a.th + base;  const double* g1 = g0 + V;
+    const double* q0 = a.pi + base;  const double* q1 = q0 + V;
+    const int tid = threadIdx.x;
+
+    // Phase 1a: interior, vectorised double2, momenta kept in registers for phase 3.
+    double2 pr0[kStepMaxUnits], pr1[kStepMaxUnits];
+    const int units = TR * (TC >> 1);
+#pragma unroll
+    for (int k = 0; k < kStepMaxUnits; ++k) {
+        const int u = tid + k * kStepThreads;
+        if (u < units) {
+            const int r = u / (TC >> 1), c = (u - r * (TC >> 1)) << 1;
+            const size_t g = (size_t)(x0 + r) * L + (y0 + c);
+            const double2 a0 = *reinterpret_cast<const double2*>(g0 + g);
+            const double2 a1 = *reinterpret_cast<const double2*>(g1 + g);
+            pr0[k] = *reinterpret_cast<const double2*>(q0 + g);
+            pr1[k] = *reinterpret_cast<const double2*>(q1 + g);
+            const int o = (r + 1) * W + (c + 1);
+            t0[o] = fma(a.drift, pr0[k].x, a0.x);  t0[o + 1] = fma(a.drift, pr0[k].y, a0.y);
+            t1[o] = fma(a.drift, pr1[k].x, a1.x);  t1[o + 1] = fma(a.drift, pr1[k].y, a1.y);
+        }
+    }
+    // Phase 1b: halo ring (rows -1 and TR over all columns, columns -1 and TC over interior rows).
+    const int ring = 2 * W + 2 * TR;
+    for (int h = tid; h < ring; h += kStepThreads) {
+        int r, c;
+        if (h < 2 * W) { r = (h < W) ? -1 : TR; c = (h < W ? h : h - W) - 1; }
+        else { const int k = h - 2 * W; r = k >> 1; c = (k & 1) ? TC : -1; }
+        const int gy = wrapi(y0 + c, L);
+        int gx = x0 + r;
+        double v0, v1;
+        if (SLAB && gx < 0) {
+            v0 = fma(a.drift, a.pi_up[gy], a.th_up[gy]);
+            v1 = fma(a.drift, a.pi_up[L + gy], a.th_up[L + gy]);
+        } else if (SLAB && gx >= Lx) {
+            v0 = fma(a.drift, a.pi_dn[gy], a.th_dn[gy]);
+            v1 = fma(a.drift, a.pi_dn[L + gy], a.th_dn[L + gy]);
+        } else {
+            gx = wrapi(gx, Lx);
+            const size_t g = (size_t)gx * L + gy;
+            v0 = fma(a.drift, q0[g], g0[g]);
+            v1 = fma(a.drift, q1[g], g1[g]);
+        }
+        t0[(r + 1) * W + (c + 1)] = v0;
+        t1[(r + 1) * W + (c + 1)] = v1;
+    }
+    __syncthreads();
+    // Phase 2: sin P on rows -1..TR-1, cols -1..TC-1.
+    for (int i = tid; i < (TR + 1) * WS; i += kStepThreads) {
+        const int r = i / WS, c = i - r * WS;       // already offset by +1 w.r.t. (-1,-1)
+        const double p = t0[r * W + c] - t1[r * W + c] - t0[r * W + c + 1] + t1[(r + 1) * W + c];
+        sp[i] = sin(p);
+    }
+    __syncthreads();
+    // Phase 3: kick + write back.
+    const double kb = a.kick * a.beta;
+    double* o0 = a.tho + base;  double* o1 = o0 + V;
+    double* w0 = a.pio + base;  double* w1 = w0 + V;
+#pragma unroll
+    for (int k = 0; k < kStepMaxUnits; ++k) {
+        const int u = tid + k * kStepThreads;
+        if (u < units) {
+            const int r = u / (TC >> 1), c = (u - r * (TC >> 1)) << 1;
+            const size_t g = (size_t)(x0 + r) * L + (y0 + c);
+            const int o = (r + 1) * W + (c + 1);
+            const int s = (r + 1) * WS + (c + 1);
+            const double s00 = sp[s], s01 = sp[s + 1], sl = sp[s - 1];
+            const double su0 = sp[s - WS], su1 = sp[s - WS + 1];
+            double2 n0, n1;
+            n0.x = fma(-kb, s00 - sl, pr0[k].x);   n0.y = fma(-kb, s01 - s00, pr0[k].y);
+            n1.x = fma(-kb, su0 - s00, pr1[k].x);  n1.y = fma(-kb, su1 - s01, pr1[k].y);
+            *reinterpret_cast<double2*>(o0 + g) = make_double2(t0[o], t0[o + 1]);
+            *reinterpret_cast<double2*>(o1 + g) = make_double2(t1[o], t1[o + 1]);
+            *reinterpret_cast<double2*>(w0 + g) = n0;
+            *reinterpret_cast<double2*>(w1 + g) = n1;
+        }
+    }
+}
+
+static int largest_divisor_leq(int n, int cap, bool even) {
+    for (int d = (cap < n ? cap : n); d >= 1; --d)
+        if (n % d == 0 && (!even || (d % 2 == 0))) return d;
+    return 1;
+}
+
+struct Tiling { int TR, TC, tiles_x, tiles_y; size_t smem; };
+static Tiling make_tiling(int Lx, int L) {
+    Tiling t;
+    t.TC = largest_divisor_leq(L, 128, true);
+    t.TR = largest_divisor_leq(Lx, 1024 / t.TC > 0 ? 1024 / t.TC : 1, false);
+    t.tiles_x = Lx / t.TR;
+    t.tiles_y = L / t.TC;
+    t.smem = (size_t)(2 * (t.TR + 2) * (t.TC + 2) + (t.TR + 1) * (t.TC + 1)) * sizeof(double);
+    return t;
+}
+
+static int launch_step(const StepArgs& in, int B, bool slab, cudaStream_t st) {
+    StepArgs a = in;
+    if (a.L < 2 || (a.L & 1)) return U1_ERR_SHAPE;
+    Tiling t = make_tiling(a.Lx, a.L);
+    a.TR = t.TR; a.TC = t.TC; a.tiles_y = t.tiles_y;
+    dim3 grid(t.tiles_x * t.tiles_y, B);
+    if (slab) k_leapfrog_step<true><<<grid, kStepThreads, t.smem, st>>>(a);
+    else      k_leapfrog_step<false><<<grid, kStepThreads, t.smem, st>>>(a);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-chain sums: [0]=sum cos(wrap P), [1]=sum wrap P, [2]=sum pi^2.  Two deterministic phases.
+// ---------------------------------------------------------------------------------------
+constexpr int kSumThreads = 256;
+constexpr int kSumRowsPerBlock = 16;
+
+__global__ void __launch_bounds__(kSumThreads)
+k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
+               const double* __restrict__ pi, double* __restrict__ partial, int Lx, int L, int nblk) {
+    __shared__ double red[3 * 32];
+    const size_t V = (size_t)Lx * L;
+    const double* t0 = th + (size_t)blockIdx.y * 2 * V;
+    const double* t1 = t0 + V;
+    const int xa = blockIdx.x * kSumRowsPerBlock;
+    const int xb = min(Lx, xa + kSumRowsPerBlock);
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < (xb - xa) * L; i += kSumThreads) {
+        const int x = xa + i / L, y = i % L;
+        const int yp = wrapi(y + 1, L);
+        double t1dn;
+        if (x + 1 < Lx) t1dn = t1[(size_t)(x + 1) * L + y];
+        else t1dn = th_dn ? th_dn[L + y] : t1[y];
+        const double w = wrap_pi(t0[(size_t)x * L + y] - t1[(size_t)x * L + y] - t0[(size_t)x * L + yp] + t1dn);
+        v[0] += cos(w);
+        v[1] += w;
+        if (pi) {
+            const double* q = pi + (size_t)blockIdx.y * 2 * V;
+            const double a = q[(size_t)x * L + y], b = q[V + (size_t)x * L + y];
+            v[2] += a * a + b * b;
+        }
+    }
+    block_sum<3>(v, red);
+    if (threadIdx.x == 0) {
+        double* o = partial + ((size_t)blockIdx.y * nblk + blockIdx.x) * 3;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    }
+}
+
+__global__ void k_finish_sums(const double* __restrict__ partial, double* __restrict__ sums, int B, int nblk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int k = 0; k < nblk; ++k) {
+        const double* p = partial + ((size_t)b * nblk + k) * 3;
+        s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    sums[(size_t)b * 3 + 0] = s0; sums[(size_t)b * 3 + 1] = s1; sums[(size_t)b * 3 + 2] = s2;
+}
+
+static inline int sum_blocks(int Lx) { return (Lx + kSumRowsPerBlock - 1) / kSumRowsPerBlock; }
+
+// sums: device [B][3]; partial: device [B][nblk][3]
+static int launch_sums(const double* th, const double* th_dn, const double* pi, double* sums,
+                       double* partial, int B, int Lx, int L, cudaStream_t st) {
+    const int nblk = sum_blocks(Lx);
+    k_partial_sums<<<dim3(nblk, B), kSumThreads, 0, st>>>(th, th_dn, pi, partial, Lx, L, nblk);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_finish_sums<<<(B + 127) / 128, 128, 0, st>>>(partial, sums, B, nblk);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+__global__ void k_scale_action(const double* __restrict__ sums, double* __restrict__ S, int B, double beta) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) S[b] = (-beta) * sums[(size_t)b * 3];
+}
+
+__global__ void k_obs_from_sums(const double* __restrict__ sums, double* __restrict__ plaq,
+                                double* __restrict__ topo, int B, double inv_vol) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (plaq) plaq[b] = sums[(size_t)b * 3] * inv_vol;
+    if (topo) topo[b] = floor(0.1 + sums[(size_t)b * 3 + 1] / kTwoPi);
+}
+
+// Metropolis decision for the streaming path (hmc_u1.py:84-97).
+__global__ void k_metropolis(const double* __restrict__ s_old, const double* __restrict__ s_new,
+                             const double* __restrict__ u_inject, uint64_t seed, uint64_t chain0,
+                             uint64_t traj, int B, double beta, double inv_vol,
+                             double* out_dH, int32_t* out_acc, double* out_H, double* out_plaq,
+                             double* out_topo, int32_t* acc_flag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* o = s_old + (size_t)b * 3;
+    const double* n = s_new + (size_t)b * 3;
+    const double H_old = (-beta) * o[0] + 0.5 * o[2];
+    const double H_new = (-beta) * n[0] + 0.5 * n[2];
+    const double dH = H_new - H_old;
+    const double u = u_inject ? u_inject[b] : philox_accept_uniform(chain_key(seed, chain0 + b), traj);
+    const bool acc = u < exp(-dH);
+    acc_flag[b] = acc ? 1 : 0;
+    const double* f = acc ? n : o;
+    if (out_dH) out_dH[b] = dH;
+    if (out_acc) out_acc[b] = acc ? 1 : 0;
+    if (out_H) out_H[b] = acc ? H_new : H_old;
+    if (out_plaq) out_plaq[b] = f[0] * inv_vol;
+    if (out_topo) out_topo[b] = floor(0.1 + f[1] / kTwoPi);
+}
+
+__global__ void k_select(double* __restrict__ theta, const double* __restrict__ theta_new,
+                         const int32_t* __restrict__ acc, size_t per_chain, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        if (acc[i / per_chain]) theta[i] = theta_new[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// SM-resident whole-trajectory kernel.  One CTA per chain; each thread owns a TX x TY tile of
+// sites (theta0, theta1, pi0, pi1 in registers for the whole trajectory).  Per leapfrog step
+// the only exchanged data are tile edges (theta' first column/row, sinP last column/row)
+// through shared memory: two __syncthreads per step, no global traffic.
+// ---------------------------------------------------------------------------------------
+struct TrajArgs {
+    double* theta;
+    const double* pi_inject; const double* u_inject;
+    uint64_t seed, chain0, traj0;
+    int n_traj, B, n_steps;
+    double beta, dt;
+    double* out_dH; int32_t* out_acc; double* out_H; double* out_plaq; double* out_topo;
+};
+
+template <int L, int TX, int TY>
+__global__ void __launch_bounds__((L / TX) * (L / TY))
+k_traj_resident(TrajArgs a) {
+    constexpr int NTX = L / TX, NTY = L / TY, NT = NTX * NTY, V = L * L;
+    static_assert(NT % 32 == 0 && TY % 2 == 0, "tile config");
+    extern __shared__ double dsm[];
+    double* colA = dsm;                       // theta0' at (x, first column of tile ty): [x][ty]
+    double* rowA = colA + L * NTY;            // theta1' at (first row of tile tx, y): [tx][j][ty]
+    double* colB = rowA + NTX * TY * NTY;     // sinP at (x, last column of tile ty)
+    double* rowB = colB + L * NTY;            // sinP at (last row of tile tx, y)
+    double* red = rowB + NTX * TY * NTY;      // 3*32 reduction scratch
+
+    const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
+    const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
+    const int b = blockIdx.x;
+    double* g0 = a.theta + (size_t)b * 2 * V;
+    double* g1 = g0 + V;
+    const PhiloxKey key = chain_key(a.seed, a.chain0 + b);
+    const double beta = a.beta, dt = a.dt, kb = a.dt * a.beta;
+
+    double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
+
+    auto publish_theta = [&]() {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) colA[(x0 + i) * NTY + ty] = th0[i][0];
+#pragma unroll
+        for (int j = 0; j < TY; ++j) rowA[(tx * TY + j) * NTY + ty] = th1[0][j];
+    };
+    auto plaquettes = [&](double (&P)[TX][TY]) {   // call after publish_theta + __syncthreads
+        double rc[TX], rr[TY];
+#pragma unroll
+        for (int i = 0; i < TX; ++i) rc[i] = colA[(x0 + i) * NTY + tyR];
+#pragma unroll
+        for (int j = 0; j < TY; ++j) rr[j] = rowA[(txD * TY + j) * NTY + ty];
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; ++j) {
+                const double right = (j + 1 < TY) ? th0[i][j + 1] : rc[i];
+                const double down = (i + 1 < TX) ? th1[i + 1][j] : rr[j];
+                P[i][j] = th0[i][j] - th1[i][j] - right + down;
+            }
+    };
+    auto hamiltonian_sums = [&](double (&v)[3]) {   // v = {sum cos wrapP, sum wrapP, sum pi^2}
+        double P[TX][TY];
+        publish_theta();
+        __syncthreads();
+        plaquettes(P);
+        v[0] = v[1] = v[2] = 0.0;
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; ++j) {
+                const double w = wrap_pi(P[i][j]);
+                v[0] += cos(w);
+                v[1] += w;
+                v[2] += p0[i][j] * p0[i][j] + p1[i][j] * p1[i][j];
+            }
+        block_sum<3>(v, red);
+    };
+
+    for (int t = 0; t < a.n_traj; ++t) {
+        const uint64_t traj = a.traj0 + (uint64_t)t;
+        // ---- load state, draw momenta ----
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; j += 2) {
+                const int g = (x0 + i) * L + y0 + j;
+                const double2 v0 = *reinterpret_cast<const double2*>(g0 + g);
+                const double2 v1 = *reinterpret_cast<const double2*>(g1 + g);
+                th0[i][j] = v0.x; th0[i][j + 1] = v0.y;
+                th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
+            }
+        if (a.pi_inject) {
+            const double* q0 = a.pi_inject + ((size_t)t * a.B + b) * 2 * V;
+            const double* q1 = q0 + V;
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j) {
+                    p0[i][j] = q0[(x0 + i) * L + y0 + j];
+                    p1[i][j] = q1[(x0 + i) * L + y0 + j];
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j)
+                    philox_site_normals(key, traj, (uint32_t)((x0 + i) * L + y0 + j), p0[i][j], p1[i][j]);
+        }
+        // ---- H_old (hmc_u1.py:84-85) ----
+        double so[3];
+        hamiltonian_sums(so);
+        const double H_old = (-beta) * so[0] + 0.5 * so[2];
+
+        // ---- leapfrog (hmc_u1.py:71-80) ----
+        for (int s = 0; s < a.n_steps; ++s) {
+            const double dr = (s == 0) ? 0.5 * dt : dt;
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j) {
+                    th0[i][j] = fma(dr, p0[i][j], th0[i][j]);
+                    th1[i][j] = fma(dr, p1[i][j], th1[i][j]);
+                }
+            publish_theta();
+            __syncthreads();
+            double S[TX][TY];
+            plaquettes(S);
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j) S[i][j] = sin(S[i][j]);
+#pragma unroll
+            for (int i = 0; i < TX; ++i) colB[(x0 + i) * NTY + ty] = S[i][TY - 1];
+#pragma unroll
+            for (int j = 0; j < TY; ++j) rowB[(tx * TY + j) * NTY + ty] = S[TX - 1][j];
+            __syncthreads();
+            double lc[TX], ur[TY];
+#pragma unroll
+            for (int i = 0; i < TX; ++i) lc[i] = colB[(x0 + i) * NTY + tyL];
+#pragma unroll
+            for (int j = 0; j < TY; ++j) ur[j] = rowB[(txU * TY + j) * NTY + ty];
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j) {
+                    const double left = (j > 0) ? S[i][j - 1] : lc[i];
+                    const double up = (i > 0) ? S[i - 1][j] : ur[j];
+                    p0[i][j] = fma(-kb, S[i][j] - left, p0[i][j]);
+                    p1[i][j] = fma(-kb, up - S[i][j], p1[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; ++j) {
+                th0[i][j] = wrap_pi(fma(0.5 * dt, p0[i][j], th0[i][j]));
+                th1[i][j] = wrap_pi(fma(0.5 * dt, p1[i][j], th1[i][j]));
+            }
+        // ---- H_new, accept/reject (hmc_u1.py:88-97) ----
+        double sn[3];
+        hamiltonian_sums(sn);
+        const double H_new = (-beta) * sn[0] + 0.5 * sn[2];
+        const double dH = H_new - H_old;
+        const double u = a.u_inject ? a.u_inject[(size_t)t * a.B + b] : philox_accept_uniform(key, traj);
+        const bool acc = u < exp(-dH);
+        if (acc) {
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; j += 2) {
+                    const int g = (x0 + i) * L + y0 + j;
+                    *reinterpret_cast<double2*>(g0 + g) = make_double2(th0[i][j], th0[i][j + 1]);
+                    *reinterpret_cast<double2*>(g1 + g) = make_double2(th1[i][j], th1[i][j + 1]);
+                }
+        }
+        if (tid == 0) {
+            const size_t o = (size_t)t * a.B + b;
+            const double* f = acc ? sn : so;
+            if (a.out_dH) a.out_dH[o] = dH;
+            if (a.out_acc) a.out_acc[o] = acc ? 1 : 0;
+            if (a.out_H) a.out_H[o] = acc ? H_new : H_old;
+            if (a.out_plaq) a.out_plaq[o] = f[0] * (1.0 / V);
+            if (a.out_topo) a.out_topo[o] = floor(0.1 + f[1] / kTwoPi);
+        }
+    }
+}
+
+static bool resident_supported(int L) { return L == 8 || L == 16 || L == 32 || L == 64; }
+
+template <int L, int TX, int TY>
+static int launch_resident_t(const TrajArgs& a, cudaStream_t st) {
+    constexpr int NTX = L / TX, NTY = L / TY;
+    constexpr size_t smem = (size_t)(2 * (L * NTY + NTX * TY * NTY) + 3 * 32) * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_traj_resident<L, TX, TY>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k_traj_resident<L, TX, TY><<<a.B, NTX * NTY, smem, st>>>(a);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+static int launch_resident(const TrajArgs& a, int L, cudaStream_t st) {
+    switch (L) {
+        case 8:  return launch_resident_t<8, 1, 2>(a, st);
+        case 16: return launch_resident_t<16, 2, 4>(a, st);
+        case 32: return launch_resident_t<32, 2, 4>(a, st);
+        case 64: return launch_resident_t<64, 2, 4>(a, st);
+        default: return U1_ERR_UNSUPPORTED;
+    }
+}
+
+static inline int ew_grid(size_t n, int threads = 256) {
+    size_t g = (n + threads - 1) / threads;
+    const size_t cap = 148 * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Workspace layout of the streaming path.
+struct PlainWs {
+    double *thA, *piA, *thB, *piB, *partial, *s_old, *s_new;
+    int32_t* acc;
+    size_t bytes;
+};
+static PlainWs carve_plain(void* ws, int B, int L) {
+    PlainWs w;
+    const size_t f = align_up((size_t)B * 2 * L * L * sizeof(double), 256);
+    const size_t part = align_up((size_t)B * sum_blocks(L) * 3 * sizeof(double), 256);
+    const size_t s3 = align_up((size_t)B * 3 * sizeof(double), 256);
+    char* p = (char*)ws;
+    w.thA = (double*)p; p += f;  w.piA = (double*)p; p += f;
+    w.thB = (double*)p; p += f;  w.piB = (double*)p; p += f;
+    w.partial = (double*)p; p += part;
+    w.s_old = (double*)p; p += s3;  w.s_new = (double*)p; p += s3;
+    w.acc = (int32_t*)p; p += align_up((size_t)B * sizeof(int32_t), 256);
+    w.bytes = (size_t)(p - (char*)ws);
+    return w;
+}
+
+}  // namespace u1
+
+using namespace u1;
+
+extern "C" {
+
+int u1_abi_version(void) { return U1_ABI_VERSION; }
+
+const char* u1_status_string(int s) {
+    switch (s) {
+        case U1_OK: return "ok";
+        case U1_ERR_ARG: return "invalid argument (null pointer or non-positive size)";
+        case U1_ERR_SHAPE: return "unsupported lattice shape (L must be even and >= 2)";
+        case U1_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case U1_ERR_HANDLE: return "bad FT handle or weight blob";
+        case U1_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+    }
+}
+
+int u1_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return (int)e;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return U1_OK;
+}
+
+long long u1_last_launch_count(void) { return g_launches; }
+
+int u1_plaquette(const double* theta, double* plaq, int B, int L, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !plaq || B <= 0 || L <= 0) return U1_ERR_ARG;
+    k_plaquette<<<ew_grid((size_t)B * L * L), 256, 0, (cudaStream_t)stream>>>(theta, plaq, B, L);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_rectangle(const double* theta, double* rect, int B, int L, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !rect || B <= 0 || L <= 0) return U1_ERR_ARG;
+    k_rectangle<<<ew_grid((size_t)B * L * L), 256, 0, (cudaStream_t)stream>>>(theta, rect, B, L);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_regularize(const double* in, double* out, size_t n, u1_stream_t stream) {
+    g_launches = 0;
+    if (!in || !out) return U1_ERR_ARG;
+    if (n == 0) return U1_OK;
+    k_regularize<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+size_t u1_workspace_bytes(int B, int L) {
+    if (B <= 0 || L <= 0) return 0;
+    return carve_plain(nullptr, B, L).bytes;
+}
+
+static int check_ws(void* ws, size_t have, size_t need) {
+    if (!ws || have < need || (reinterpret_cast<uintptr_t>(ws) & 255u)) return U1_ERR_WORKSPACE;
+    return U1_OK;
+}
+
+int u1_observables(const double* theta, double* plaq_mean, double* topo, int B, int L,
+                   void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || B <= 0 || L <= 0) return U1_ERR_ARG;
+    U1_TRY(check_ws(ws, ws_bytes, u1_workspace_bytes(B, L)));
+    PlainWs w = carve_plain(ws, B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    U1_TRY(launch_sums(theta, nullptr, nullptr, w.s_new, w.partial, B, L, L, st));
+    k_obs_from_sums<<<(B + 127) / 128, 128, 0, st>>>(w.s_new, plaq_mean, topo, B, 1.0 / ((double)L * L));
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_action(const double* theta, double* S, int B, int L, double beta,
+              void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !S || B <= 0 || L <= 0) return U1_ERR_ARG;
+    U1_TRY(check_ws(ws, ws_bytes, u1_workspace_bytes(B, L)));
+    PlainWs w = carve_plain(ws, B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    U1_TRY(launch_sums(theta, nullptr, nullptr, w.s_new, w.partial, B, L, L, st));
+    k_scale_action<<<(B + 127) / 128, 128, 0, st>>>(w.s_new, S, B, beta);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_force(const double* theta, double* force, int B, int L, double beta, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !force || B <= 0 || L <= 0) return U1_ERR_ARG;
+    k_force<<<ew_grid((size_t)B * L * L), 256, 0, (cudaStream_t)stream>>>(theta, force, B, L, beta);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_momenta(double* pi, uint64_t seed, uint64_t chain0, uint64_t traj, int B, int L,
+               u1_stream_t stream) {
+    g_launches = 0;
+    if (!pi || B <= 0 || L <= 0) return U1_ERR_ARG;
+    k_momenta<<<ew_grid((size_t)B * L * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain0, traj, B, L);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_leapfrog_step(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                     int B, int L, double beta, double drift, double kick, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0) return U1_ERR_ARG;
+    if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    StepArgs a{};
+    a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
+    a.Lx = L; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
+    return launch_step(a, B, false, (cudaStream_t)stream);
+}
+
+// n_steps fused steps ping-ponging between (thA,piA) and (thB,piB); returns where the result is.
+static int leapfrog_stream(const double* th_in, const double* pi_in, PlainWs& w, int B, int L,
+                           double beta, double dt, int n_steps, cudaStream_t st,
+                           const double** th_res, const double** pi_res) {
+    const double* ct = th_in;
+    const double* cp = pi_in;
+    for (int s = 0; s < n_steps; ++s) {
+        double* ot = (s & 1) ? w.thB : w.thA;
+        double* op = (s & 1) ? w.piB : w.piA;
+        StepArgs a{};
+        a.th = ct; a.pi = cp; a.tho = ot; a.pio = op;
+        a.Lx = L; a.L = L; a.beta = beta; a.drift = (s == 0) ? 0.5 * dt : dt; a.kick = dt;
+        U1_TRY(launch_step(a, B, false, st));
+        ct = ot; cp = op;
+    }
+    *th_res = ct; *pi_res = cp;
+    return U1_OK;
+}
+
+int u1_leapfrog(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                int B, int L, double beta, double dt, int n_steps,
+                void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || n_steps < 1) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    U1_TRY(check_ws(ws, ws_bytes, u1_workspace_bytes(B, L)));
+    PlainWs w = carve_plain(ws, B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *ct, *cp;
+    U1_TRY(leapfrog_stream(theta_in, pi_in, w, B, L, beta, dt, n_steps, st, &ct, &cp));
+    const size_t n = (size_t)B * 2 * L * L;
+    k_final_drift<<<ew_grid(n), 256, 0, st>>>(ct, cp, theta_out, 0.5 * dt, n);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    if (pi_out != cp) {
+        cudaError_t e = cudaMemcpyAsync(pi_out, cp, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return U1_OK;
+}
+
+int u1_trajectory(double* theta, const double* pi_inject, const double* u_inject,
+                  uint64_t seed, uint64_t chain0, uint64_t traj0, int n_traj,
+                  int B, int L, double beta, double dt, int n_steps,
+                  double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                  double* out_topo, int path, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool resident = (path == 2) || (path == 0 && resident_supported(L));
+    if (resident) {
+        if (!resident_supported(L)) return U1_ERR_UNSUPPORTED;
+        TrajArgs a{};
+        a.theta = theta; a.pi_inject = pi_inject; a.u_inject = u_inject;
+        a.seed = seed; a.chain0 = chain0; a.traj0 = traj0;
+        a.n_traj = n_traj; a.B = B; a.n_steps = n_steps; a.beta = beta; a.dt = dt;
+        a.out_dH = out_dH; a.out_acc = out_accept; a.out_H = out_H; a.out_plaq = out_plaq; a.out_topo = out_topo;
+        return launch_resident(a, L, st);
+    }
+    U1_TRY(check_ws(ws, ws_bytes, u1_workspace_bytes(B, L)));
+    PlainWs w = carve_plain(ws, B, L);
+    const size_t per = (size_t)2 * L * L, n = (size_t)B * per;
+    const double inv_vol = 1.0 / ((double)L * L);
+    for (int t = 0; t < n_traj; ++t) {
+        const uint64_t traj = traj0 + (uint64_t)t;
+        const double* pi0;
+        if (pi_inject) pi0 = pi_inject + (size_t)t * n;
+        else {
+            k_momenta<<<ew_grid((size_t)B * L * L), 256, 0, st>>>(w.piB, seed, chain0, traj, B, L);
+            count_launch();
+            U1_CHECK_LAUNCH();
+            pi0 = w.piB;   // consumed by step 0 (which writes thA/piA) before piB is overwritten
+        }
+        U1_TRY(launch_sums(theta, nullptr, pi0, w.s_old, w.partial, B, L, L, st));
+        const double *ct, *cp;
+        U1_TRY(leapfrog_stream(theta, pi0, w, B, L, beta, dt, n_steps, st, &ct, &cp));
+        double* fin = (ct == w.thA) ? w.thB : w.thA;
+        k_final_drift<<<ew_grid(n), 256, 0, st>>>(ct, cp, fin, 0.5 * dt, n);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        U1_TRY(launch_sums(fin, nullptr, cp, w.s_new, w.partial, B, L, L, st));
+        const size_t o = (size_t)t * B;
+        k_metropolis<<<(B + 127) / 128, 128, 0, st>>>(
+            w.s_old, w.s_new, u_inject ? u_inject + o : nullptr, seed, chain0, traj, B, beta, inv_vol,
+            out_dH ? out_dH + o : nullptr, out_accept ? out_accept + o : nullptr,
+            out_H ? out_H + o : nullptr, out_plaq ? out_plaq + o : nullptr,
+            out_topo ? out_topo + o : nullptr, w.acc);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        k_select<<<ew_grid(n), 256, 0, st>>>(theta, fin, w.acc, per, n);
+        count_launch();
+        U1_CHECK_LAUNCH();
+    }
+    return U1_OK;
+}
+
+int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
+                          const double* theta_up, const double* pi_up,
+                          const double* theta_dn, const double* pi_dn,
+                          double* theta_out, double* pi_out,
+                          int Lx, int L, double beta, double drift, double kick,
+                          u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_up || !pi_up || !theta_dn || !pi_dn || !theta_out || !pi_out ||
+        Lx <= 0 || L <= 0)
+        return U1_ERR_ARG;
+    if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    StepArgs a{};
+    a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
+    a.th_up = theta_up; a.pi_up = pi_up; a.th_dn = theta_dn; a.pi_dn = pi_dn;
+    a.Lx = Lx; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
+    return launch_step(a, 1, true, (cudaStream_t)stream);
+}
+
+int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, double* sums,
+                 int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !theta_dn || !sums || Lx <= 0 || L <= 0) return U1_ERR_ARG;
+    const size_t need = (size_t)sum_blocks(Lx) * 3 * sizeof(double);
+    U1_TRY(check_ws(ws, ws_bytes, need));
+    return launch_sums(theta, theta_dn, pi, sums, (double*)ws, 1, Lx, L, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""HMC_U1 with the reference's surface (2d_u1_cluster/hmc_u1.py:7-237), computed by hand-written
+sm_100a kernels through the C ABI in include/u1hmc.h.
+
+Differences a reference user should know about (all deliberate):
+  * arithmetic is fp64 on the GPU regardless of the caller's dtype; `device` names where the
+    caller's tensors live ("cpu": host buffers in/out, copies inside the call; "cuda": resident);
+  * every method also accepts a leading chain axis: theta [B,2,L,L] -> per-chain results [B];
+  * momenta / accept draws come from an on-device Philox4x32-10 stream keyed by
+    (seed, global chain id, trajectory index); `metropolis_step(theta, pi=..., u=...)` injects
+    the draws instead (parity tests, golden-log replay);
+  * the constructor does not touch torch's global default dtype/device/seed (hmc_u1.py:49-51).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev
+
+try:                                    # progress bars are cosmetic
+    from tqdm import tqdm
+except Exception:                       # pragma: no cover
+    def tqdm(x, **_):
+        return x
+
+
+class HMC_U1:
+    def __init__(self, lattice_size, beta, n_thermalization_steps, n_steps, step_size, device="cuda",
+                 if_tune_step_size=True, n_chains: Optional[int] = None, seed: int = 1331,
+                 chain_offset: int = 0, kernel_path: int = 0, verbose: bool = False):
+        """Same leading arguments as hmc_u1.py:8-17.  Extra keyword arguments:
+        n_chains     batch of independent chains (None: single chain, reference return types)
+        seed         Philox seed (default echoes torch.manual_seed(1331), hmc_u1.py:51)
+        chain_offset global id of this process's first chain (chain sharding across GPUs)
+        kernel_path  0 auto, 1 streaming step kernels, 2 SM-resident trajectory kernel"""
+        if lattice_size < 2 or lattice_size % 2:
+            raise ValueError("lattice_size must be even and >= 2")
+        self.lattice_size = int(lattice_size)
+        self.beta = float(beta)
+        self.n_thermalization_steps = int(n_thermalization_steps)
+        self.n_steps = int(n_steps)
+        self.dt = float(step_size)
+        self.device = torch.device(device)
+        self.if_tune_step_size = if_tune_step_size
+        self.n_chains = n_chains
+        self.seed = int(seed)
+        self.chain_offset = int(chain_offset)
+        self.kernel_path = int(kernel_path)
+        self.verbose = verbose
+        self.traj_counter = 0              # Philox trajectory index, advances with every step
+        self.gpu_launches = 0
+        self._lib = _lib.load()            # fail loudly now if the CUDA library is missing
+        self._dev = require_cuda(self.device if self.device.type == "cuda" else None)
+
+    # ------------------------------------------------------------------ helpers
+    def _print(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def _stage(self, t: torch.Tensor):
+        tb, single = as_batch(t)
+        d = to_dev(tb, self._dev)
+        check_field(d)
+        return d, single
+
+    def _back(self, t: torch.Tensor, like: torch.Tensor, single: bool = False):
+        if single:
+            t = t[0]
+        return t if like.device == t.device else t.to(like.device)
+
+    def _ws(self, B: int):
+        return WS.get(self._dev, self._lib.u1_workspace_bytes(B, self.lattice_size))
+
+    # ------------------------------------------------------------------ reference surface
+    def initialize(self):
+        """hmc_u1.py:53-54 (cold start)."""
+        L = self.lattice_size
+        shape = [2, L, L] if self.n_chains is None else [self.n_chains, 2, L, L]
+        return torch.zeros(shape, dtype=torch.float64, device=self.device)
+
+    def action(self, theta):
+        """hmc_u1.py:56-63."""
+        d, single = self._stage(theta)
+        B, L = check_field(d)
+        out = torch.empty(B, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = self._ws(B)
+            _lib.check(self._lib.u1_action(d.data_ptr(), out.data_ptr(), B, L, self.beta, ws, nb,
+                                           stream_ptr(self._dev)), "u1_action")
+        return self._back(out, theta, single)
+
+    def force(self, theta):
+        """hmc_u1.py:65-69."""
+        d, single = self._stage(theta)
+        B, L = check_field(d)
+        out = torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.u1_force(d.data_ptr(), out.data_ptr(), B, L, self.beta,
+                                          stream_ptr(self._dev)), "u1_force")
+        return self._back(out, theta, single)
+
+    def leapfrog(self, theta, pi):
+        """hmc_u1.py:71-80."""
+        d, single = self._stage(theta)
+        p, _ = self._stage(pi)
+        B, L = check_field(d)
+        to, po = torch.empty_like(d), torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            ws, nb = self._ws(B)
+            _lib.check(self._lib.u1_leapfrog(d.data_ptr(), p.data_ptr(), to.data_ptr(), po.data_ptr(), B, L,
+                                             self.beta, self.dt, self.n_steps, ws, nb,
+                                             stream_ptr(self._dev)), "u1_leapfrog")
+        return self._back(to, theta, single), self._back(po, theta, single)
+
+    def trajectories(self, theta_dev: torch.Tensor, n_traj: int = 1, pi=None, u=None, want_obs: bool = True):
+        """n_traj Metropolis steps on the device-resident batch `theta_dev` ([B,2,L,L] fp64, updated
+        IN PLACE).  Returns dict of device tensors [n_traj,B]: dH, accept, H, plaq, topo."""
+        B, L = check_field(theta_dev)
+        dev = self._dev
+        out = {k: torch.empty((n_traj, B), dtype=torch.float64, device=dev) for k in ("dH", "H", "plaq", "topo")}
+        out["accept"] = torch.empty((n_traj, B), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            ws, nb = self._ws(B)
+            _lib.check(self._lib.u1_trajectory(
+                theta_dev.data_ptr(), ptr(pi), ptr(u), self.seed, self.chain_offset, self.traj_counter, n_traj,
+                B, L, self.beta, self.dt, self.n_steps,
+                out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
+                out["plaq"].data_ptr() if want_obs else None, out["topo"].data_ptr() if want_obs else None,
+                self.kernel_path, ws, nb, stream_ptr(dev)), "u1_trajectory")
+        self.gpu_launches += _lib.last_launch_count()
+        self.traj_counter += n_traj
+        return out
+
+    def metropolis_step(self, theta, pi=None, u=None):
+        """hmc_u1.py:82-97.  Single chain: (theta, bool, float) like the reference;
+        batch: (theta [B,2,L,L], accepted bool[B], H[B])."""
+        d, single = self._stage(theta)
+        if d.data_ptr() == theta.data_ptr():
+            d = d.clone()                       # the reference never mutates its argument
+        B, L = check_field(d)
+        pi_d = None if pi is None else to_dev(as_batch(pi)[0], self._dev).reshape(1, B, 2, L, L)
+        u_d = None if u is None else to_dev(torch.as_tensor(u, dtype=torch.float64).reshape(-1), self._dev)
+        r = self.trajectories(d, 1, pi_d, u_d, want_obs=False)
+        if single:
+            acc, H = r["accept"][0, 0].item(), r["H"][0, 0].item()      # host sync, as in the reference
+            return self._back(d, theta, True), bool(acc), H
+        return self._back(d, theta), self._back(r["accept"][0].bool(), theta), self._back(r["H"][0], theta)
+
+    def tune_step_size(self, n_tune_steps=2000, target_rate=0.65, target_tolerance=0.15,
+                       initial_step_size=0.2, max_attempts=10, theta=None):
+        """hmc_u1.py:99-161: binary search on dt.  As in the reference, every trial trajectory
+        starts from the same `theta` (the returned state is discarded, hmc_u1.py:132).  With a
+        batch of chains the acceptance rate is the mean over chains."""
+        theta = self.initialize() if theta is None else theta
+        base, _ = self._stage(theta)
+        self.dt = initial_step_size
+        step_min, step_max = 1e-6, 1.0
+        best_dt, best_diff = self.dt, float("inf")
+        rate = 0.0
+        for attempt in range(max_attempts):
+            acc = torch.zeros((), dtype=torch.float64, device=self._dev)
+            for _ in range(n_tune_steps):
+                r = self.trajectories(base.clone(), 1, want_obs=False)
+                acc += r["accept"].double().mean()
+            rate = (acc / n_tune_steps).item()
+            diff = abs(rate - target_rate)
+            self._print(f"Step size: {self.dt:.6f}, Acceptance rate: {rate:.2%}")
+            if diff < best_diff:
+                best_dt, best_diff = self.dt, diff
+            if diff <= target_tolerance:
+                self._print(f"Found good step size: {self.dt:.6f}")
+                break
+            if rate > target_rate:
+                step_min = self.dt
+                self.dt = min((self.dt + step_max) / 2, step_max)
+            else:
+                step_max = self.dt
+                self.dt = max((self.dt + step_min) / 2, step_min)
+        if abs(rate - target_rate) > target_tolerance:
+            self._print(f"Using best found step size: {best_dt:.6f}")
+            self.dt = best_dt
+
+    def thermalize(self):
+        """hmc_u1.py:163-196: rough thermalisation, optional tuning, restart from cold, then
+        n_thermalization_steps trajectories recording the plaquette BEFORE each step."""
+        theta = self.initialize()
+        d, single = self._stage(theta)
+        d = d.clone()
+        n = self.n_thermalization_steps
+        if n > 0:
+            self.trajectories(d, n, want_obs=False)
+        if self.if_tune_step_size:
+            self.tune_step_size(initial_step_size=self.dt, theta=d)
+        else:
+            self._print(f">>> Using step size: {self.dt:.2f}")
+        d.zero_()
+        B = d.shape[0]
+        if n == 0:
+            return self._back(d, theta, single), [], 0.0
+        from .utils import plaq_mean_from_field
+        plaq0 = plaq_mean_from_field(d).reshape(1, B)
+        r = self.trajectories(d, n)
+        plaq = torch.cat([plaq0, r["plaq"][:-1]], dim=0)       # value before each step
+        acc = r["accept"].double().mean(dim=0)
+        if single:
+            return self._back(d, theta, True), plaq[:, 0].tolist(), acc[0].item()
+        return self._back(d, theta), plaq.cpu(), acc.cpu()
+
+    def run(self, n_iterations, theta, store_interval=1, save_config=True):
+        """hmc_u1.py:198-237.  Observables are accumulated on the device and read back once.
+        Single chain: Python lists exactly like the reference; batch: tensors [n_store,B]."""
+        d, single = self._stage(theta)
+        d = d.clone()
+        B, L = check_field(d)
+        theta_ls, plaq, topo, ham, acc = [], [], [], [], []
+        done = 0
+        si = int(store_interval)
+        while done < n_iterations:
+            if save_config:      # snapshot right after each stored iteration
+                chunk = 1 if done % si == 0 else min(si - done % si, n_iterations - done)
+            else:                # no snapshots: many trajectories per launch
+                chunk = min(512, n_iterations - done)
+            r = self.trajectories(d, chunk)
+            for k in range(chunk):
+                if (done + k) % si == 0:
+                    plaq.append(r["plaq"][k]); topo.append(r["topo"][k]); ham.append(r["H"][k])
+                    if save_config:
+                        theta_ls.append(self._back(d.clone(), theta, single))
+            acc.append(r["accept"].double().sum(dim=0))
+            done += chunk
+        rate = torch.stack(acc).sum(dim=0) / n_iterations
+        plaq, topo, ham = torch.stack(plaq), torch.stack(topo), torch.stack(ham)
+        if single:
+            return theta_ls, plaq[:, 0].tolist(), rate[0].item(), topo[:, 0].tolist(), ham[:, 0].tolist()
+        return theta_ls, plaq.cpu(), rate.cpu(), topo.cpu(), ham.cpu()

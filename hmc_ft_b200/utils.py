@@ -1,0 +1,160 @@
+"""Lattice primitives with the reference's names (2d_u1_cluster/utils.py:21-222), computed by the
+sm_100a library.  Inputs may be host or device tensors of any float dtype; arithmetic is fp64 on
+the GPU and results come back on the input's device.  Host-side helpers (masks, analytic
+expectations, autocorrelation) are plain numpy/torch index logic with no device work."""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev
+
+
+def set_seed(seed: int) -> None:
+    """utils.py:11-19."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def _run_field_op(name, theta, out_shape_fn):
+    lib = _lib.load()
+    dev = require_cuda(theta.device if theta.is_cuda else None)
+    tb, single = as_batch(theta)
+    d = to_dev(tb, dev)
+    B, L = check_field(d)
+    out = torch.empty(out_shape_fn(B, L), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(getattr(lib, name)(d.data_ptr(), out.data_ptr(), B, L, stream_ptr(dev)), name)
+    out = out[0] if single else out
+    return out if theta.is_cuda else out.to(theta.device)
+
+
+def plaq_from_field(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:143-150.  [2,L,L] -> [L,L] (also accepts [B,2,L,L])."""
+    return _run_field_op("u1_plaquette", theta, lambda B, L: (B, L, L))
+
+
+def plaq_from_field_batch(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:118-127.  [B,2,L,L] -> [B,L,L]."""
+    return _run_field_op("u1_plaquette", theta, lambda B, L: (B, L, L))
+
+
+def rect_from_field_batch(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:129-141.  [B,2,L,L] -> [B,2,L,L]."""
+    return _run_field_op("u1_rectangle", theta, lambda B, L: (B, 2, L, L))
+
+
+def regularize(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:182-187: wrap to [-pi, pi)."""
+    lib = _lib.load()
+    dev = require_cuda(theta.device if theta.is_cuda else None)
+    d = to_dev(theta, dev)
+    out = torch.empty_like(d)
+    with torch.cuda.device(dev):
+        _lib.check(lib.u1_regularize(d.data_ptr(), out.data_ptr(), d.numel(), stream_ptr(dev)), "u1_regularize")
+    return out if theta.is_cuda else out.to(theta.device)
+
+
+def _observables(theta: torch.Tensor):
+    lib = _lib.load()
+    dev = require_cuda(theta.device if theta.is_cuda else None)
+    tb, single = as_batch(theta)
+    d = to_dev(tb, dev)
+    B, L = check_field(d)
+    plaq = torch.empty(B, dtype=torch.float64, device=dev)
+    topo = torch.empty(B, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws, nb = WS.get(dev, lib.u1_workspace_bytes(B, L))
+        _lib.check(lib.u1_observables(d.data_ptr(), plaq.data_ptr(), topo.data_ptr(), B, L, ws, nb,
+                                      stream_ptr(dev)), "u1_observables")
+    if single:
+        plaq, topo = plaq[0], topo[0]
+    if not theta.is_cuda:
+        plaq, topo = plaq.to(theta.device), topo.to(theta.device)
+    return plaq, topo
+
+
+def plaq_mean_from_field(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:173-180."""
+    return _observables(theta)[0]
+
+
+def topo_from_field(theta: torch.Tensor) -> torch.Tensor:
+    """utils.py:189-196."""
+    return _observables(theta)[1]
+
+
+# ---- host-side index logic (no arithmetic on fields) ----
+def get_field_mask(index: int, batch_size: int, L: int) -> torch.Tensor:
+    """utils.py:21-50."""
+    m = torch.zeros((batch_size, 2, L, L), dtype=torch.bool)
+    mu, k = divmod(index, 4)
+    m[:, mu, (k >> 1) & 1::2, k & 1::2] = True
+    return m
+
+
+def get_plaq_mask(index: int, batch_size: int, L: int) -> torch.Tensor:
+    """utils.py:52-80."""
+    m = torch.zeros((batch_size, L, L), dtype=torch.bool)
+    if index < 4:
+        m[:, (1 if index < 2 else 0)::2, :] = True
+    else:
+        m[:, :, (1 if index in (4, 6) else 0)::2] = True
+    return m
+
+
+def get_rect_mask(index: int, batch_size: int, L: int) -> torch.Tensor:
+    """utils.py:82-115."""
+    m = torch.zeros((batch_size, 2, L, L), dtype=torch.bool)
+    k = index % 4
+    a, b = (k >> 1) & 1, k & 1          # parity of the active links of this subset
+    if index < 4:                        # only R1 kept
+        m[:, 1, (1 - a)::2, :] = True
+        m[:, 1, a::2, (1 - b)::2] = True
+    else:                                # only R0 kept
+        m[:, 0, :, (1 - b)::2] = True
+        m[:, 0, (1 - a)::2, b::2] = True
+    return m
+
+
+def plaq_mean_theory(beta: float) -> float:
+    """utils.py:152-171: I1(beta)/I0(beta)."""
+    from scipy.special import i0, i1
+    return float(i1(beta) / i0(beta))
+
+
+def chi_infinity(beta: float) -> float:
+    """utils.py:207-222."""
+    from scipy.integrate import quad
+    num, _ = quad(lambda p: (p / (2 * math.pi)) ** 2 * math.exp(beta * math.cos(p)), -math.pi, math.pi)
+    den, _ = quad(lambda p: math.exp(beta * math.cos(p)), -math.pi, math.pi)
+    return num / den
+
+
+def auto_from_chi(topo, max_lag: int, beta: float, volume: int) -> np.ndarray:
+    """utils.py:224-262: Gamma(d) = 1 - <(Q_t - Q_{t+d})^2> / (2 V chi_inf)."""
+    topo = np.round(np.asarray(topo)).astype(int)
+    chi = chi_infinity(beta)
+    out = np.ones(max_lag + 1)
+    for d in range(1, max_lag + 1):
+        out[d] = 1 - np.mean((topo[:-d] - topo[d:]) ** 2) / (2 * volume * chi)
+    return out
+
+
+def auto_by_def(topo, max_lag: int) -> np.ndarray:
+    """utils.py:264-298."""
+    topo = np.round(np.asarray(topo)).astype(int)
+    mean, var = np.mean(topo), np.var(topo)
+    if var == 0:
+        return np.ones(max_lag + 1)
+    out = np.ones(max_lag + 1)
+    for d in range(1, max_lag + 1):
+        out[d] = np.mean((topo[:-d] - mean) * (topo[d:] - mean)) / var
+    return out

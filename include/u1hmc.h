@@ -1,0 +1,153 @@
+/* u1hmc.h — C ABI of the B200 (sm_100a) 2D U(1) HMC / FT-HMC hot path.
+ *
+ * The reference (Greyyy-HJC/hmc_ft) is pure Python/torch and has no FFI layer; the seam it
+ * offers is the Python class surface (HMC_U1, HMC_U1_FT, FieldTransformation, utils.*).
+ * Each entry point below replaces the torch-op sequence of one reference method and cites it
+ * (paths relative to 2d_u1_cluster/).  hmc_ft_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *  - All field pointers are DEVICE pointers owned by the caller: contiguous fp64, row-major
+ *    theta[b][mu][x][y], b<B chains, mu<2, x,y<L (y fastest) — the reference's [2,L,L] with a
+ *    leading chain axis.  L must be even for the FT entry points (utils.py:21-115 masks).
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and
+ *    allocation-free: scratch comes in through (ws, ws_bytes); query with *_workspace_bytes().
+ *  - Return value: 0 ok, <0 argument error (U1_ERR_*), >0 a cudaError_t.  Nothing throws.
+ *  - No global/constant-memory state.  FT weights live in an opaque per-handle host object and
+ *    travel to the kernels as launch parameters.
+ */
+#ifndef U1HMC_H
+#define U1HMC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define U1_ABI_VERSION 1
+#define U1_OK 0
+#define U1_ERR_ARG (-1)         /* null pointer / non-positive size            */
+#define U1_ERR_SHAPE (-2)       /* unsupported L (odd L on an FT entry point)  */
+#define U1_ERR_WORKSPACE (-3)   /* workspace too small or misaligned           */
+#define U1_ERR_HANDLE (-4)      /* bad FT handle / weight blob                 */
+#define U1_ERR_UNSUPPORTED (-5)
+
+typedef void* u1_stream_t;
+
+int u1_abi_version(void);
+const char* u1_status_string(int status);
+/* SM count and compute capability of the current device (fails loudly off sm_100). */
+int u1_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------- L1a lattice primitives (utils.py) ---------------- */
+/* utils.py:118-127,143-150  plaq_from_field[_batch]: P[b][x][y]. */
+int u1_plaquette(const double* theta, double* plaq, int B, int L, u1_stream_t stream);
+/* utils.py:129-141  rect_from_field_batch: R[b][2][x][y]. */
+int u1_rectangle(const double* theta, double* rect, int B, int L, u1_stream_t stream);
+/* utils.py:182-187  regularize, elementwise over n doubles (in may equal out). */
+int u1_regularize(const double* in, double* out, size_t n, u1_stream_t stream);
+/* utils.py:173-180,189-196  plaq_mean_from_field / topo_from_field: per-chain outputs. */
+int u1_observables(const double* theta, double* plaq_mean, double* topo, int B, int L,
+                   void* ws, size_t ws_bytes, u1_stream_t stream);
+
+/* ---------------- HMC_U1 (hmc_u1.py) ---------------- */
+size_t u1_workspace_bytes(int B, int L);
+/* hmc_u1.py:56-63  action(theta) -> S[b]. */
+int u1_action(const double* theta, double* S, int B, int L, double beta,
+              void* ws, size_t ws_bytes, u1_stream_t stream);
+/* hmc_u1.py:65-69  force(theta) (autograd of the action) -> F[b][2][x][y]. */
+int u1_force(const double* theta, double* force, int B, int L, double beta, u1_stream_t stream);
+/* hmc_u1.py:71-80  leapfrog(theta, pi): n_steps force evaluations, half drifts at both ends,
+ * theta wrapped at the end.  One fused drift+force+kick kernel per step (HBM streaming).
+ * In-place is allowed (theta_out==theta_in, pi_out==pi_in) only through the workspace path:
+ * ws must hold u1_workspace_bytes(B,L). */
+int u1_leapfrog(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                int B, int L, double beta, double dt, int n_steps,
+                void* ws, size_t ws_bytes, u1_stream_t stream);
+/* One leapfrog step as a single kernel: theta' = theta + drift*pi ; pi' = pi - kick*F(theta').
+ * (The body of hmc_u1.py:75-77.)  Out-of-place only. */
+int u1_leapfrog_step(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                     int B, int L, double beta, double drift, double kick, u1_stream_t stream);
+/* Philox4x32-10 momenta pi[b] ~ N(0,1) for global chain ids chain0..chain0+B-1 and trajectory
+ * index `traj` (replaces torch.randn_like, hmc_u1.py:83). */
+int u1_momenta(double* pi, uint64_t seed, uint64_t chain0, uint64_t traj, int B, int L,
+               u1_stream_t stream);
+/* hmc_u1.py:82-97 metropolis_step, `n_traj` times back to back, plus the stored-step
+ * observables of run() (hmc_u1.py:219-225).  theta is updated in place.
+ *   pi_inject  [n_traj][B][2][L][L] or NULL (NULL: Philox momenta on device)
+ *   u_inject   [n_traj][B]           or NULL (NULL: Philox uniforms on device)
+ * Outputs are [n_traj][B]: dH, accept (int32 0/1), H (H_new if accepted else H_old, as the
+ * reference returns), plaq and topo of the state after the step.  Any output may be NULL.
+ * path: 0 auto, 1 force the streaming (one kernel per leapfrog step) path,
+ *       2 force the SM-resident whole-trajectory kernel (L in {8,16,32,64}). */
+int u1_trajectory(double* theta, const double* pi_inject, const double* u_inject,
+                  uint64_t seed, uint64_t chain0, uint64_t traj0, int n_traj,
+                  int B, int L, double beta, double dt, int n_steps,
+                  double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                  double* out_topo, int path, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* Number of kernel launches the last u1_* / u1ft_* call on this host thread issued
+ * (bench.py reports it as gpu_launches). */
+long long u1_last_launch_count(void);
+
+/* ---------------- slab (domain-decomposed) variants for one large lattice ----------------
+ * The lattice is split along x into slabs of Lx rows (global width L).  The caller supplies the
+ * halo rows it received from its ring neighbours (NCCL send/recv through torch.distributed):
+ *   theta_up  [2][L]  : last row of the upper neighbour  (x = -1), values BEFORE this step's drift
+ *   pi_up     [2][L]
+ *   theta_dn  [2][L]  : first row of the lower neighbour (x = Lx)
+ *   pi_dn     [2][L]
+ * Since drift is local, halos of (theta, pi) before the step are enough to advance one step. */
+int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
+                          const double* theta_up, const double* pi_up,
+                          const double* theta_dn, const double* pi_dn,
+                          double* theta_out, double* pi_out,
+                          int Lx, int L, double beta, double drift, double kick,
+                          u1_stream_t stream);
+/* Partial sums of one slab: sums[0]=sum cos(wrap P), sums[1]=sum wrap P, sums[2]=sum pi^2
+ * (pi may be NULL).  theta_dn as above (first row of the lower neighbour). */
+int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, double* sums,
+                 int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+
+/* ---------------- FieldTransformation / HMC_U1_FT ---------------- */
+typedef struct u1ft_handle_s* u1ft_handle_t;
+/* field_trans_opt.py:654-692 (_load_best_model) + cnn_model_opt.py:6-247.
+ * n_res_blocks: 0 = jointCNN_simple, 1 = jointCNN_rnet1, 3 = jointCNN_rnet3 (any 0..8 accepted).
+ * weights: HOST fp64 blob, for subset s=0..7, for each conv layer in forward order:
+ *   W[o][c][3][3] (torch Conv2d layout) then b[o].  First layer 6->12, the rest 12->12. */
+int u1ft_create(u1ft_handle_t* out, int n_res_blocks, const double* weights, size_t n_doubles);
+int u1ft_destroy(u1ft_handle_t h);
+size_t u1ft_weight_count(int n_res_blocks);
+/* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
+size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);
+/* field_trans_opt.py:219-243 forward / field_transformation and :284-383 compute_jac_logdet in
+ * one pass (one CNN evaluation per subset).  theta_ori and logdet may each be NULL. */
+int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
+                 int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* field_trans_opt.py:137-217  ft_phase(theta, index) -> Delta[b][2][x][y] (diagnostic surface). */
+int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
+               int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* hmc_u1_ft.py:101-125  new_action = S(F(theta)) - logdet.  Optional extra outputs. */
+int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* theta_ori,
+                double* logdet, int B, int L, double beta,
+                void* ws, size_t ws_bytes, u1_stream_t stream);
+/* hmc_u1_ft.py:128-152  new_force: hand-derived reverse pass (no autograd). S_ft may be NULL. */
+int u1ft_force(u1ft_handle_t h, const double* theta, double* force, double* S_ft,
+               int B, int L, double beta, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* hmc_u1_ft.py:154-179 leapfrog with new_force. */
+int u1ft_leapfrog(u1ft_handle_t h, const double* theta_in, const double* pi_in,
+                  double* theta_out, double* pi_out, int B, int L, double beta, double dt,
+                  int n_steps, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* hmc_u1_ft.py:181-209 metropolis_step x n_traj + stored-step observables of run()
+ * (hmc_u1_ft.py:348-358: plaq/topo of regularize(F(theta))).  Same conventions as u1_trajectory;
+ * theta_ori_out [B][2][L][L] (may be NULL) receives F(theta) of the final state. */
+int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, const double* u_inject,
+                    uint64_t seed, uint64_t chain0, uint64_t traj0, int n_traj,
+                    int B, int L, double beta, double dt, int n_steps,
+                    double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                    double* out_topo, double* theta_ori_out,
+                    void* ws, size_t ws_bytes, u1_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* U1HMC_H */

@@ -1,0 +1,178 @@
+"""GPU parity of the plain HMC path (C ABI through hmc_ft_b200) against the CPU oracle and the
+reference-generated golden vectors.  Tolerances: 1e-12 relative on action / force (north star);
+leapfrog/dH after n steps are compared at 1e-9 (round-off of a 50-step symplectic map)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import u1_oracle as O
+
+
+def rel(a, b):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hmc_ft_b200 as hb
+    assert torch.cuda.is_available()
+    return hb
+
+
+@pytest.mark.parametrize("tag", ["L6_b1p5", "L16_b2", "L64_b6"])
+def test_golden_action_force_leapfrog(hb, golden_dir, tag):
+    from hmc_ft_b200 import utils as U
+    z = np.load(os.path.join(golden_dir, f"plain_{tag}.npz"))
+    L, beta, n, dt = int(z["L"]), float(z["beta"]), int(z["n_steps"]), float(z["dt"])
+    th = torch.tensor(z["theta"], dtype=torch.float64, device="cuda")
+    pi = torch.tensor(z["pi"], dtype=torch.float64, device="cuda")
+    h = hb.HMC_U1(L, beta, 0, n, dt, device="cuda", if_tune_step_size=False)
+    S = h.action(th)
+    assert S.dim() == 0 and abs(S.item() - float(z["action"])) <= 1e-12 * abs(float(z["action"]))
+    assert rel(h.force(th), z["force"]) < 1e-12
+    assert rel(U.plaq_from_field(th), z["plaq_field"]) < 1e-15
+    assert rel(U.regularize(th * 3.7), z["regularized"]) < 1e-15
+    assert abs(U.plaq_mean_from_field(th).item() - float(z["plaq"])) < 1e-14
+    assert U.topo_from_field(th).item() == float(z["topo"])
+    th2, pi2 = h.leapfrog(th, pi)
+    assert rel(th2, z["theta_out"]) < 1e-9 and rel(pi2, z["pi_out"]) < 1e-9
+    # host-buffer call path (device="cpu": H2D / D2H inside the call)
+    hc = hb.HMC_U1(L, beta, 0, n, dt, device="cpu", if_tune_step_size=False)
+    Fh = hc.force(torch.tensor(z["theta"]))
+    assert Fh.device.type == "cpu" and rel(Fh, z["force"]) < 1e-12
+
+
+@pytest.mark.parametrize("L,B,path", [(8, 5, 2), (16, 3, 2), (32, 4, 2), (64, 3, 2), (64, 3, 1),
+                                      (16, 2, 1), (6, 3, 1), (12, 2, 1), (130, 1, 1)])
+def test_trajectory_vs_oracle(hb, L, B, path):
+    """Fused trajectory (both kernel paths) with injected pi/u against the oracle:
+    dH, accept, H, plaq, topo, final state."""
+    g = torch.Generator().manual_seed(100 + L)
+    beta, n, dt = 2.5, 7, 0.11
+    th = (torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
+    pi = torch.randn(B, 2, L, L, generator=g, dtype=torch.float64)
+    u = torch.rand(B, generator=g, dtype=torch.float64)
+    o = O.PlainHMCOracle(L, beta, n, dt)
+    th_o, acc_o, H_o, dH_o = o.metropolis_step(th, pi, u)
+    h = hb.HMC_U1(L, beta, 0, n, dt, device="cuda", if_tune_step_size=False, n_chains=B, kernel_path=path)
+    d = th.cuda().clone()
+    r = h.trajectories(d, 1, pi.cuda().reshape(1, B, 2, L, L).contiguous(), u.cuda())
+    assert rel(r["dH"][0], dH_o) < 1e-10
+    assert torch.equal(r["accept"][0].cpu().bool(), acc_o)
+    assert rel(r["H"][0], H_o) < 1e-11
+    assert rel(d, th_o) < 1e-10
+    assert rel(r["plaq"][0], O.plaq_mean(th_o)) < 1e-11
+    assert torch.equal(r["topo"][0].cpu(), O.topo_charge(th_o))
+    assert h.gpu_launches > 0
+
+
+def test_replay_reference_golden_log(hb, golden_dir):
+    """tests/test.out: every trajectory restarted from the oracle's state (no error build-up),
+    momenta/uniforms from torch's CPU generator seeded like tests/hmc_2DU1.py."""
+    with open(os.path.join(golden_dir, "test_out_head.json")) as f:
+        G = json.load(f)
+    L, beta, n = G["L"], G["beta"], G["nstep"]
+    dt = G["tau"] / n
+    torch.manual_seed(G["seed"])
+    x = torch.zeros(2, L, L, dtype=torch.float64)
+    o = O.PlainHMCOracle(L, beta, n, dt)
+    for path in (2, 1):
+        torch.manual_seed(G["seed"])
+        x = torch.zeros(2, L, L, dtype=torch.float64)
+        h = hb.HMC_U1(L, beta, 0, n, dt, device="cuda", if_tune_step_size=False, kernel_path=path)
+        for row in G["rows"][:8]:
+            p = torch.randn_like(x)
+            u = torch.rand([], dtype=torch.float64)
+            xo, acc, _, dH = o.metropolis_step(x[None], p[None], u[None])
+            d = x.cuda()[None].clone()
+            r = h.trajectories(d, 1, p.cuda().reshape(1, 1, 2, L, L), u.cuda().reshape(1))
+            assert abs(r["dH"][0, 0].item() - row["dH"]) <= 2e-7 * max(1.0, abs(row["dH"]))
+            assert bool(r["accept"][0, 0].item()) == row["accept"]
+            assert abs(r["plaq"][0, 0].item() - row["plaq"]) < 5e-8
+            assert r["topo"][0, 0].item() == row["topo"]
+            assert abs(r["dH"][0, 0].item() - dH.item()) < 1e-9
+            x = xo[0]
+
+
+def test_philox_stream_bit_exact(hb):
+    """Device Philox momenta / uniforms against the numpy restatement (oracle) and N(0,1) moments."""
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    B, L, seed, chain0, traj = 3, 16, 1331, 7, 5
+    pi = torch.empty(B, 2, L, L, dtype=torch.float64, device="cuda")
+    _lib.check(lib.u1_momenta(pi.data_ptr(), seed, chain0, traj, B, L, torch.cuda.current_stream().cuda_stream))
+    for b in range(B):
+        want = O.philox_momenta(seed, chain0 + b, traj, L)
+        assert np.max(np.abs(pi[b].cpu().numpy() - want)) < 1e-13
+    big = torch.empty(64, 2, 64, 64, dtype=torch.float64, device="cuda")
+    _lib.check(lib.u1_momenta(big.data_ptr(), 1, 0, 0, 64, 64, torch.cuda.current_stream().cuda_stream))
+    assert abs(big.mean().item()) < 5e-3 and abs(big.std().item() - 1) < 5e-3
+    assert abs((big ** 4).mean().item() - 3) < 0.05
+
+
+def test_chain_results_independent_of_batching(hb):
+    """Philox keyed by global chain id: chains 4..7 run alone == chains 4..7 inside a batch of 8."""
+    L, beta, n, dt = 32, 3.0, 10, 0.1
+    a = hb.HMC_U1(L, beta, 0, n, dt, n_chains=8, if_tune_step_size=False)
+    b = hb.HMC_U1(L, beta, 0, n, dt, n_chains=4, if_tune_step_size=False, chain_offset=4)
+    ta = torch.zeros(8, 2, L, L, dtype=torch.float64, device="cuda")
+    tb = torch.zeros(4, 2, L, L, dtype=torch.float64, device="cuda")
+    ra = a.trajectories(ta, 5)
+    rb = b.trajectories(tb, 5)
+    assert torch.equal(ta[4:], tb) and torch.equal(ra["dH"][:, 4:], rb["dH"])
+    # streaming path produces the same chain up to round-off
+    c = hb.HMC_U1(L, beta, 0, n, dt, n_chains=4, if_tune_step_size=False, chain_offset=4, kernel_path=1)
+    tc = torch.zeros(4, 2, L, L, dtype=torch.float64, device="cuda")
+    rc = c.trajectories(tc, 1)
+    assert rel(rc["dH"], rb["dH"][:1]) < 1e-9
+
+
+def test_ensemble_plaquette_matches_theory(hb):
+    """<plaq> = I1(beta)/I0(beta) within statistical error (utils.py:152-171), B=512 chains at full
+    C2 lattice size; also energy conservation <exp(-dH)> = 1."""
+    from hmc_ft_b200.utils import plaq_mean_theory
+    L, beta, n, dt, B = 64, 6.0, 50, 0.06, 512
+    h = hb.HMC_U1(L, beta, 0, n, dt, n_chains=B, if_tune_step_size=False)
+    d = torch.zeros(B, 2, L, L, dtype=torch.float64, device="cuda")
+    h.trajectories(d, 60, want_obs=False)
+    r = h.trajectories(d, 20)
+    plaq = r["plaq"].mean(dim=0)                      # per-chain average over 20 trajectories
+    mean, err = plaq.mean().item(), plaq.std().item() / math.sqrt(B)
+    assert abs(mean - plaq_mean_theory(beta)) < 5 * err + 1e-5, (mean, err, plaq_mean_theory(beta))
+    acc = r["accept"].double().mean().item()
+    assert 0.4 < acc < 0.9
+    e = torch.exp(-r["dH"]).mean().item()
+    assert abs(e - 1) < 0.05
+    assert torch.all(r["topo"] == torch.round(r["topo"]))
+
+
+def test_reference_style_run_and_thermalize(hb):
+    h = hb.HMC_U1(16, 2.0, 5, 10, 0.1, device="cpu", if_tune_step_size=False)
+    theta, plaq_ls, acc = h.thermalize()
+    assert theta.shape == (2, 16, 16) and theta.device.type == "cpu" and len(plaq_ls) == 5 and plaq_ls[0] == 1.0
+    cfg, plaq, rate, topo, ham = h.run(6, theta, store_interval=2, save_config=True)
+    assert len(cfg) == 3 and len(plaq) == 3 and len(topo) == 3 and len(ham) == 3 and 0 <= rate <= 1
+    th, ok, H = h.metropolis_step(theta)
+    assert isinstance(ok, bool) and isinstance(H, float) and th.shape == theta.shape
+
+
+def test_argument_errors(hb):
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    assert lib.u1_force(None, None, 1, 8, 1.0, None) == -1
+    t = torch.zeros(1, 2, 7, 7, dtype=torch.float64, device="cuda")
+    assert lib.u1_trajectory(t.data_ptr(), None, None, 0, 0, 0, 1, 1, 7, 1.0, 0.1, 2,
+                             None, None, None, None, None, 0, None, 0, None) == -2
+    t = torch.zeros(1, 2, 12, 12, dtype=torch.float64, device="cuda")
+    assert lib.u1_trajectory(t.data_ptr(), None, None, 0, 0, 0, 1, 1, 12, 1.0, 0.1, 2,
+                             None, None, None, None, None, 2, None, 0, None) == -5
+    assert lib.u1_trajectory(t.data_ptr(), None, None, 0, 0, 0, 1, 1, 12, 1.0, 0.1, 2,
+                             None, None, None, None, None, 1, None, 0, None) == -3
