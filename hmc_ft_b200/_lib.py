@@ -29,11 +29,13 @@ SIGNATURES = {
     "u1_trajectory": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _i, _i, _i, _d, _d, _i,
                            _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "u1_last_launch_count": (C.c_longlong, []),
+    "u1_fp64_probe": (_i, [_vp, _i, _i, _vp]),
     "u1_slab_leapfrog_step": (_i, [_vp] * 8 + [_i, _i, _d, _d, _d, _vp]),
     "u1_slab_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_create": (_i, [C.POINTER(_vp), _i, _vp, _sz]),
     "u1ft_destroy": (_i, [_vp]),
     "u1ft_weight_count": (_sz, [_i]),
+    "u1ft_set_chunk_sites": (C.c_longlong, [C.c_longlong]),
     "u1ft_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "u1ft_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_phase": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),

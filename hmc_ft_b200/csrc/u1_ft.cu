@@ -1,14 +1,933 @@
-// placeholder: FT entry points arrive in the next milestone
+// Field-transformed HMC on sm_100a (fp64): the 8-subset CNN field transformation, its Jacobian
+// log-det and the hand-derived reverse pass (no autograd), behind the C ABI of include/u1hmc.h.
+//
+// Reference semantics: 2d_u1_cluster/field_trans_opt.py:110-383, cnn_model_opt.py:6-247,
+// hmc_u1_ft.py:77-209,348-358, utils.py:21-141.
+//
+// Structure per subset k (theta^(k) -> theta^(k+1)):
+//   k_ft_features : X[6] = sin/cos of the masked plaquette / rectangle angles
+//   k_conv<...>   : 3x3 circular convolutions, one launch per layer, weights travel as a
+//                   __grid_constant__ launch parameter so every DFMA reads its weight from the
+//                   constant bank; epilogue = bias (+skip) + exact-erf GELU (+ GELU' stored for
+//                   the reverse pass) or the final atan/2pi
+//   k_ft_update   : Delta / log(1+J) on the active links
+// Reverse pass (k = 7..0): k_ft_update_bwd -> transposed convolutions (same kernel, flipped
+// weights, epilogue (conv + skip) * GELU') -> k_ft_feat_bwd -> k_ft_scatter.
+// The FT path is FP64-FMA bound; activations of a chunk of chains are sized to stay in L2.
+#include <new>
+#include <vector>
+#include <cstdlib>
+#include <atomic>
 #include "u1_common.cuh"
-extern "C" {
-int u1ft_create(u1ft_handle_t*, int, const double*, size_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_destroy(u1ft_handle_t) { return U1_ERR_UNSUPPORTED; }
-size_t u1ft_weight_count(int) { return 0; }
-size_t u1ft_workspace_bytes(u1ft_handle_t, int, int, int) { return 0; }
-int u1ft_forward(u1ft_handle_t, const double*, double*, double*, int, int, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_phase(u1ft_handle_t, const double*, int, double*, int, int, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_action(u1ft_handle_t, const double*, double*, double*, double*, int, int, double, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_force(u1ft_handle_t, const double*, double*, double*, int, int, double, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_leapfrog(u1ft_handle_t, const double*, const double*, double*, double*, int, int, double, double, int, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
-int u1ft_trajectory(u1ft_handle_t, double*, const double*, const double*, uint64_t, uint64_t, uint64_t, int, int, int, double, double, int, double*, int32_t*, double*, double*, double*, double*, void*, size_t, u1_stream_t) { return U1_ERR_UNSUPPORTED; }
+
+namespace u1 {
+
+constexpr int kW = 12;               // hidden width of every jointCNN_* (cnn_model_opt.py)
+constexpr int kXC = 6;               // input feature channels
+constexpr int kConvThreads = 128;
+
+template <int CIN, int COUT>
+struct ConvP {
+    double w[CIN * 9 * COUT];        // w[(c*9 + tap)*COUT + o]
+    double b[COUT];
+};
+
+enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
+
+// exact-erf GELU (nn.GELU default) and its derivative.
+__device__ __forceinline__ void gelu_and_grad(double z, double& a, double& d, bool want_d) {
+    const double cdf = 0.5 * (1.0 + erf(z * 0.70710678118654752440));
+    a = z * cdf;
+    d = want_d ? fma(z * 0.39894228040143267794, exp(-0.5 * z * z), cdf) : 0.0;
 }
+
+// out[o](x,y) = sum_{c,i,j} w[c][i*3+j][o] * in[c]((x+i-1)%L, (y+j-1)%L)   (+ epilogue)
+//   EPI_GELU : z = acc + b (+ add);  out = GELU(z);  dout = GELU'(z)            (dout may be null)
+//   EPI_FINAL: z = acc + b;  y = GELU(z);  out = atan(y)/pi/2;  dout = GELU'(z)/((1+y^2) 2pi)
+//   EPI_BWD  : out = (acc (+ add)) (* mul)
+template <int CIN, int COUT, int EPI>
+__global__ void __launch_bounds__(kConvThreads)
+k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
+       const double* __restrict__ add, const double* __restrict__ mul,
+       double* __restrict__ out, double* __restrict__ dout, int nsites, int L) {
+    const int s = blockIdx.x * kConvThreads + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V;
+    const int x = r / L, y = r - x * L;
+    const int xr[3] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x == L - 1 ? 0 : x + 1) * L};
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * CIN * V;
+
+    double acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i * 3 + j] = pc[xr[i] + yc[j]];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) acc[o] = fma(p.w[(c * 9 + t) * COUT + o], v[t], acc[o]);
+    }
+    const size_t ob = (size_t)b * COUT * V + r;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        const size_t idx = ob + (size_t)o * V;
+        if (EPI == EPI_BWD) {
+            double rv = acc[o];
+            if (add) rv += add[idx];
+            if (mul) rv *= mul[idx];
+            out[idx] = rv;
+        } else {
+            double z = acc[o] + p.b[o];
+            if (EPI == EPI_GELU && add) z += add[idx];
+            double a, d;
+            gelu_and_grad(z, a, d, dout != nullptr);
+            if (EPI == EPI_GELU) {
+                out[idx] = a;
+                if (dout) dout[idx] = d;
+            } else {
+                out[idx] = atan(a) / kPi / 2;                      // cnn_model_opt.py:46
+                if (dout) dout[idx] = d / ((1.0 + a * a) * kTwoPi);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Lattice angle helpers (utils.py:118-141) with periodic wrap; x,y may be off by up to 2.
+// ---------------------------------------------------------------------------------------
+struct Lat {
+    const double* t0; const double* t1; int L;
+    __device__ __forceinline__ double a0(int x, int y) const { return t0[wrapi(x, L) * L + wrapi(y, L)]; }
+    __device__ __forceinline__ double a1(int x, int y) const { return t1[wrapi(x, L) * L + wrapi(y, L)]; }
+    __device__ __forceinline__ double P(int x, int y) const {
+        return a0(x, y) - a1(x, y) - a0(x, y + 1) + a1(x + 1, y);
+    }
+    __device__ __forceinline__ double R0(int x, int y) const {
+        return a0(x, y) + a0(x + 1, y) + a1(x + 2, y) - a0(x + 1, y + 1) - a0(x, y + 1) - a1(x, y);
+    }
+    __device__ __forceinline__ double R1(int x, int y) const {
+        return a0(x, y) + a1(x + 1, y) + a1(x + 1, y + 1) - a0(x, y + 2) - a1(x, y + 1) - a1(x, y);
+    }
+    __device__ __forceinline__ int loc(int x, int y) const { return wrapi(x, L) * L + wrapi(y, L); }
+};
+
+struct Subset { int mu, a, b; };
+__host__ __device__ __forceinline__ Subset subset_of(int k) {   // utils.py:21-50
+    Subset s; s.mu = k >> 2; s.a = (k >> 1) & 1; s.b = k & 1; return s;
+}
+
+// The six angles of the active link (mu; x,y), their signs in Delta, their dense K channel and
+// their location (field_trans_opt.py:137-217).  Angles 0,1 are plaquettes, 2..5 rectangles.
+struct LinkTerms { double A[6]; int loc[6]; };
+__device__ __forceinline__ void link_terms(const Lat& g, int mu, int x, int y, LinkTerms& t) {
+    if (mu == 0) {
+        t.A[0] = g.P(x, y);          t.loc[0] = g.loc(x, y);
+        t.A[1] = g.P(x, y - 1);      t.loc[1] = g.loc(x, y - 1);
+        t.A[2] = g.R0(x - 1, y);     t.loc[2] = g.loc(x - 1, y);
+        t.A[3] = g.R0(x - 1, y - 1); t.loc[3] = g.loc(x - 1, y - 1);
+        t.A[4] = g.R0(x, y);         t.loc[4] = g.loc(x, y);
+        t.A[5] = g.R0(x, y - 1);     t.loc[5] = g.loc(x, y - 1);
+    } else {
+        t.A[0] = g.P(x, y);          t.loc[0] = g.loc(x, y);
+        t.A[1] = g.P(x - 1, y);      t.loc[1] = g.loc(x - 1, y);
+        t.A[2] = g.R1(x, y - 1);     t.loc[2] = g.loc(x, y - 1);
+        t.A[3] = g.R1(x - 1, y - 1); t.loc[3] = g.loc(x - 1, y - 1);
+        t.A[4] = g.R1(x, y);         t.loc[4] = g.loc(x, y);
+        t.A[5] = g.R1(x - 1, y);     t.loc[5] = g.loc(x - 1, y);
+    }
+}
+// sign of term j in Delta: mu=0: -,+,-,+,-,+ ; mu=1: +,-,+,-,+,-
+__device__ __forceinline__ double term_sign(int mu, int j) { return ((j & 1) ^ mu) ? 1.0 : -1.0; }
+// dense K channel of term j: K0 -> 0..3, K1 -> 4..11
+__device__ __forceinline__ int term_channel(int mu, int j) {
+    return (j < 2) ? (2 * mu + j) : (4 + 4 * mu + (j - 2));
+}
+
+// ---------------------------------------------------------------------------------------
+// Features (field_trans_opt.py:110-131)
+// ---------------------------------------------------------------------------------------
+__global__ void k_ft_features(const double* __restrict__ th, double* __restrict__ X, int k, int nsites, int L) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
+    const Subset ss = subset_of(k);
+    Lat g{th + (size_t)b * 2 * V, th + (size_t)b * 2 * V + V, L};
+    const bool active_site = ((x & 1) == ss.a) && ((y & 1) == ss.b);
+    const bool mP = ss.mu == 0 ? ((x & 1) != ss.a) : ((y & 1) != ss.b);      // utils.py:52-80
+    const bool mR = !active_site;                                             // utils.py:82-115
+    double sP = 0.0, cP = 1.0, sR = 0.0, cR = 1.0;
+    if (mP) sincos(g.P(x, y), &sP, &cP);
+    if (mR) sincos(ss.mu == 0 ? g.R1(x, y) : g.R0(x, y), &sR, &cR);
+    double* o = X + (size_t)b * kXC * V + r;
+    o[0] = sP;
+    o[(size_t)V] = cP;
+    o[(size_t)2 * V] = ss.mu == 0 ? 0.0 : sR;     // sin(m0 R0)
+    o[(size_t)3 * V] = ss.mu == 0 ? sR : 0.0;     // sin(m1 R1)
+    o[(size_t)4 * V] = ss.mu == 0 ? 1.0 : cR;     // cos(m0 R0)
+    o[(size_t)5 * V] = ss.mu == 0 ? cR : 1.0;     // cos(m1 R1)
+}
+
+// ---------------------------------------------------------------------------------------
+// Subset update: theta^(k+1) = theta^(k) + Delta_k, log-det partial sums
+// (field_trans_opt.py:137-217, 284-383).  mode 0: out = theta + Delta ; mode 1: out = Delta.
+// ---------------------------------------------------------------------------------------
+constexpr int kUpdThreads = 256;
+
+__global__ void __launch_bounds__(kUpdThreads)
+k_ft_update(const double* __restrict__ th, const double* __restrict__ K, double* __restrict__ out,
+            double* __restrict__ partial, int k, int L, int nblk, int mode) {
+    __shared__ double red[32];
+    const int V = L * L;
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * kUpdThreads + threadIdx.x;
+    const Subset ss = subset_of(k);
+    double ld[1] = {0.0};
+    if (r < V) {
+        const int x = r / L, y = r - x * L;
+        const double* t0 = th + (size_t)b * 2 * V;
+        Lat g{t0, t0 + V, L};
+        double o0 = mode ? 0.0 : t0[r], o1 = mode ? 0.0 : t0[V + r];
+        if (((x & 1) == ss.a) && ((y & 1) == ss.b)) {
+            LinkTerms t;
+            link_terms(g, ss.mu, x, y, t);
+            const double* Kb = K + (size_t)b * kW * V + r;
+            double d[6], j[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                double sn, cs;
+                sincos(t.A[q], &sn, &cs);
+                const double kq = Kb[(size_t)term_channel(ss.mu, q) * V];
+                d[q] = kq * (term_sign(ss.mu, q) * sn);
+                j[q] = kq * (-cs);
+            }
+            // same association as the reference: (plaq0+plaq1) + (((r0+r1)+r2)+r3)
+            const double delta = (d[0] + d[1]) + (((d[2] + d[3]) + d[4]) + d[5]);
+            const double jac = (j[0] + j[1]) + (((j[2] + j[3]) + j[4]) + j[5]);
+            if (ss.mu == 0) o0 += delta; else o1 += delta;
+            ld[0] = log(1.0 + jac);
+        }
+        double* ob = out + (size_t)b * 2 * V;
+        ob[r] = o0;
+        ob[V + r] = o1;
+    }
+    if (partial) {
+        block_sum<1>(ld, red);
+        if (threadIdx.x == 0) partial[(size_t)b * nblk + blockIdx.x] = ld[0];
+    }
+}
+
+// logdet[b] (+)= sum of partials, fixed order.
+__global__ void k_ft_logdet_accum(const double* __restrict__ partial, double* __restrict__ logdet,
+                                  int B, int nblk, int first) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += partial[(size_t)b * nblk + i];
+    logdet[b] = first ? s : logdet[b] + s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Reverse pass of one subset.
+//   g      : dS/dtheta^(k+1)                         [B][2][V]
+//   zbar   : adjoint of the final conv's pre-activation  [B][12][V]  (written densely)
+//   AP, AR : adjoints of the plaquette / (update-type) rectangle angles, [B][V], pre-zeroed
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kUpdThreads)
+k_ft_update_bwd(const double* __restrict__ th, const double* __restrict__ K,
+                const double* __restrict__ dfin, const double* __restrict__ g,
+                double* __restrict__ zbar, double* __restrict__ AP, double* __restrict__ AR,
+                int k, int nsites, int L) {
+    const int s = blockIdx.x * kUpdThreads + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
+    const Subset ss = subset_of(k);
+    double zb[kW];
+#pragma unroll
+    for (int c = 0; c < kW; ++c) zb[c] = 0.0;
+    if (((x & 1) == ss.a) && ((y & 1) == ss.b)) {
+        const double* t0 = th + (size_t)b * 2 * V;
+        Lat gl{t0, t0 + V, L};
+        LinkTerms t;
+        link_terms(gl, ss.mu, x, y, t);
+        const double* Kb = K + (size_t)b * kW * V + r;
+        const double* db = dfin + (size_t)b * kW * V + r;
+        double sn[6], cs[6], kq[6], jq[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            sincos(t.A[q], &sn[q], &cs[q]);
+            kq[q] = Kb[(size_t)term_channel(ss.mu, q) * V];
+            jq[q] = kq[q] * (-cs[q]);
+        }
+        const double jac = (jq[0] + jq[1]) + (((jq[2] + jq[3]) + jq[4]) + jq[5]);
+        const double ga = g[(size_t)b * 2 * V + (size_t)ss.mu * V + r];   // adjoint of Delta
+        const double gb = -1.0 / (1.0 + jac);                             // adjoint of J  (S_FT has -log(1+J))
+        double* APb = AP + (size_t)b * V;
+        double* ARb = AR + (size_t)b * V;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double sg = term_sign(ss.mu, q);
+            const int ch = term_channel(ss.mu, q);
+            const double kbar = ga * sg * sn[q] - gb * cs[q];
+            zb[ch] = kbar * db[(size_t)ch * V];
+            const double abar = kq[q] * (ga * sg * cs[q] + gb * sn[q]);
+            if (q < 2) APb[t.loc[q]] = abar; else ARb[t.loc[q]] = abar;
+        }
+    }
+    double* zo = zbar + (size_t)b * kW * V + r;
+#pragma unroll
+    for (int c = 0; c < kW; ++c) zo[(size_t)c * V] = zb[c];
+}
+
+// Total plaquette adjoint PT[b][V] of subset k: update angles (AP, AR) + CNN features (Xbar).
+__global__ void k_ft_feat_bwd(const double* __restrict__ th, const double* __restrict__ Xbar,
+                              const double* __restrict__ AP, const double* __restrict__ AR,
+                              double* __restrict__ PT, int k, int nsites, int L) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
+    const Subset ss = subset_of(k);
+    const double* t0 = th + (size_t)b * 2 * V;
+    Lat g{t0, t0 + V, L};
+    const double* xb = Xbar + (size_t)b * kXC * V;
+    const double* ARb = AR + (size_t)b * V;
+    double pt = AP[(size_t)b * V + r];
+    const bool mP = ss.mu == 0 ? ((x & 1) != ss.a) : ((y & 1) != ss.b);
+    if (mP) {
+        double sn, cs;
+        sincos(g.P(x, y), &sn, &cs);
+        pt += xb[r] * cs - xb[(size_t)V + r] * sn;
+    }
+    // rectangle adjoint of the CNN-feature type at location (xx,yy)
+    auto cnn_rect = [&](int xx, int yy) -> double {
+        const int xw = wrapi(xx, L), yw = wrapi(yy, L);
+        if (((xw & 1) == ss.a) && ((yw & 1) == ss.b)) return 0.0;       // masked out
+        const int q = xw * L + yw;
+        double sn, cs;
+        if (ss.mu == 0) {            // features use R1: channels 3 (sin), 5 (cos)
+            sincos(g.R1(xw, yw), &sn, &cs);
+            return xb[(size_t)3 * V + q] * cs - xb[(size_t)5 * V + q] * sn;
+        } else {                     // features use R0: channels 2 (sin), 4 (cos)
+            sincos(g.R0(xw, yw), &sn, &cs);
+            return xb[(size_t)2 * V + q] * cs - xb[(size_t)4 * V + q] * sn;
+        }
+    };
+    // R0(x,y)=P(x,y)+P(x+1,y) -> P(x,y) collects R0bar(x,y)+R0bar(x-1,y);
+    // R1(x,y)=P(x,y)+P(x,y+1) -> P(x,y) collects R1bar(x,y)+R1bar(x,y-1).
+    if (ss.mu == 0) {   // update angles are R0 (AR), CNN angles are R1
+        pt += ARb[r] + ARb[g.loc(x - 1, y)];
+        pt += cnn_rect(x, y) + cnn_rect(x, y - 1);
+    } else {            // update angles are R1 (AR), CNN angles are R0
+        pt += ARb[r] + ARb[g.loc(x, y - 1)];
+        pt += cnn_rect(x, y) + cnn_rect(x - 1, y);
+    }
+    PT[(size_t)b * V + r] = pt;
+}
+
+// g_out = g_in + dP/dtheta^T PT:  th0(x,y): +PT(x,y) - PT(x,y-1);  th1(x,y): -PT(x,y) + PT(x-1,y).
+__global__ void k_ft_scatter(const double* __restrict__ gin, const double* __restrict__ PT,
+                             double* __restrict__ gout, int nsites, int L) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
+    const double* p = PT + (size_t)b * V;
+    const double c = p[r];
+    const double l = p[x * L + wrapi(y - 1, L)];
+    const double u = p[wrapi(x - 1, L) * L + y];
+    const size_t o = (size_t)b * 2 * V + r;
+    gout[o] = gin[o] + (c - l);
+    gout[o + V] = gin[o + V] + (u - c);
+}
+
+// y = y + a*x (elementwise)
+__global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, double a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = fma(a, x[i], y[i]);
+}
+__global__ void k_axpy_wrap(double* __restrict__ y, const double* __restrict__ x, double a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = wrap_pi(fma(a, x[i], y[i]));
+}
+
+// sums3[b] = {sum cos(wrap P), sum wrap P, sum pi^2}; one CTA per chain (L <= ~256 in practice).
+__global__ void __launch_bounds__(256)
+k_chain_sums(const double* __restrict__ th, const double* __restrict__ pi, double* __restrict__ sums, int L) {
+    __shared__ double red[3 * 32];
+    const int V = L * L, b = blockIdx.x;
+    const double* t0 = th + (size_t)b * 2 * V;
+    Lat g{t0, t0 + V, L};
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int r = threadIdx.x; r < V; r += blockDim.x) {
+        const int x = r / L, y = r - x * L;
+        const double w = wrap_pi(g.P(x, y));
+        v[0] += cos(w);
+        v[1] += w;
+        if (pi) {
+            const double a = pi[(size_t)b * 2 * V + r], c = pi[(size_t)b * 2 * V + V + r];
+            v[2] += a * a + c * c;
+        }
+    }
+    block_sum<3>(v, red);
+    if (threadIdx.x == 0) { sums[b * 3] = v[0]; sums[b * 3 + 1] = v[1]; sums[b * 3 + 2] = v[2]; }
+}
+
+// plain force with the reference's wrap (initial adjoint dS/dtheta^(8)), cf. u1_plain.cu k_force.
+__global__ void k_plain_force(const double* __restrict__ th, double* __restrict__ F, int nsites, int L, double beta) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int V = L * L;
+    const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
+    const double* t0 = th + (size_t)b * 2 * V;
+    Lat g{t0, t0 + V, L};
+    const double sp = sin(wrap_pi(g.P(x, y)));
+    F[(size_t)b * 2 * V + r] = beta * (sp - sin(wrap_pi(g.P(x, y - 1))));
+    F[(size_t)b * 2 * V + V + r] = beta * (-sp + sin(wrap_pi(g.P(x - 1, y))));
+}
+
+// H = -beta*sums[0] - logdet + 0.5*sums[2]  -> Hout[b]; also S_ft
+__global__ void k_ft_hamiltonian(const double* __restrict__ sums, const double* __restrict__ logdet,
+                                 double* __restrict__ S_ft, double* __restrict__ H, int B, double beta) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double s = (-beta) * sums[b * 3] - logdet[b];
+    if (S_ft) S_ft[b] = s;
+    if (H) H[b] = s + 0.5 * sums[b * 3 + 2];
+}
+
+__global__ void k_ft_metropolis(const double* __restrict__ H_old, const double* __restrict__ H_new,
+                                const double* __restrict__ sums_old, const double* __restrict__ sums_new,
+                                const double* __restrict__ u_inject, uint64_t seed, uint64_t chain0,
+                                uint64_t traj, int B, double inv_vol, double* out_dH, int32_t* out_acc,
+                                double* out_H, double* out_plaq, double* out_topo, int32_t* acc_flag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double dH = H_new[b] - H_old[b];
+    const double u = u_inject ? u_inject[b] : philox_accept_uniform(chain_key(seed, chain0 + b), traj);
+    const bool acc = u < exp(-dH);
+    acc_flag[b] = acc ? 1 : 0;
+    const double* f = (acc ? sums_new : sums_old) + b * 3;
+    if (out_dH) out_dH[b] = dH;
+    if (out_acc) out_acc[b] = acc ? 1 : 0;
+    if (out_H) out_H[b] = acc ? H_new[b] : H_old[b];
+    if (out_plaq) out_plaq[b] = f[0] * inv_vol;
+    if (out_topo) out_topo[b] = floor(0.1 + f[1] / kTwoPi);
+}
+
+// dst[b] = src[b] where acc[b] (per-chain select), n elements per chain
+__global__ void k_select_chain(double* __restrict__ dst, const double* __restrict__ src,
+                               const int32_t* __restrict__ acc, size_t per_chain, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (acc[i / per_chain]) dst[i] = src[i];
+}
+
+__global__ void k_momenta_ft(double* __restrict__ pi, uint64_t seed, uint64_t chain0, uint64_t traj, int nsites, int V) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int b = s / V, site = s - b * V;
+    double n0, n1;
+    philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, n0, n1);
+    pi[(size_t)b * 2 * V + site] = n0;
+    pi[(size_t)b * 2 * V + V + site] = n1;
+}
+
+}  // namespace u1
+
+using namespace u1;
+
+// ---------------------------------------------------------------------------------------
+// Host side: handle, workspace carving, orchestration
+// ---------------------------------------------------------------------------------------
+struct u1ft_handle_s {
+    uint32_t magic;
+    int n_res, n_layers;                                  // n_layers = 2 + 2*n_res
+    std::vector<ConvP<kXC, kW>> f0;                       // [8] first layer (6->12)
+    std::vector<ConvP<kW, kW>> f;                         // [8][n_layers-1]
+    std::vector<ConvP<kW, kXC>> b0;                       // [8] transposed first layer (12->6)
+    std::vector<ConvP<kW, kW>> bt;                        // [8][n_layers-1] transposed
+};
+constexpr uint32_t kMagic = 0x55314654u;  // "U1FT"
+
+static inline bool handle_ok(u1ft_handle_t h) { return h && h->magic == kMagic; }
+static inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+static inline int blocks_for(size_t n, int t) { return (int)((n + t - 1) / t); }
+static inline int ew_grid_ft(size_t n) {
+    size_t g = (n + 255) / 256;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+static std::atomic<long long> g_chunk_sites{-1};
+static long long chunk_sites() {
+    long long t = g_chunk_sites.load();
+    if (t < 0) {
+        const char* e = getenv("U1FT_CHUNK_SITES");
+        t = e ? atoll(e) : 303104;            // 74 chains at L=64: 2368 CTAs of 128 = 2 waves of 148x8
+        if (t < 1) t = 1;
+        g_chunk_sites.store(t);
+    }
+    return t;
+}
+static int chunk_chains(int B, int L) {
+    const long long target = chunk_sites();
+    long long c = target / ((long long)L * L);
+    if (c < 1) c = 1;
+    if (c > B) c = B;
+    return (int)c;
+}
+
+struct FtWs {
+    double* th[9];        // theta^(0..8)                     [C][2][V]
+    double* X;            // features / Xbar                  [C][6][V]
+    double* A;            // activation ping                  [C][12][V]
+    double* Bf;           // activation pong                  [C][12][V]
+    double* Kk[8];        // K of each subset                 [C][12][V]
+    double* D;            // GELU' per subset per layer       [8][n_layers][C][12][V]
+    double* AP; double* AR; double* PT;                      // [C][V]
+    double* g0; double* g1;                                   // adjoint ping-pong [C][2][V]
+    double* partial;      // logdet partials                  [C][nblk]
+    double* logdet; double* sums_old; double* sums_new; double* H_old; double* H_new;   // [C](x3)
+    double* th_new; double* pi; double* force;                // trajectory state  [C][2][V]
+    int32_t* acc;
+    size_t bytes;
+};
+
+static FtWs carve_ft(void* ws, int n_layers, int C, int L, bool backward) {
+    FtWs w{};
+    const size_t V = (size_t)L * L;
+    const size_t f2 = al((size_t)C * 2 * V * 8), f6 = al((size_t)C * kXC * V * 8), f12 = al((size_t)C * kW * V * 8);
+    const size_t f1 = al((size_t)C * V * 8);
+    const int nblk = blocks_for(V, kUpdThreads);
+    char* p = (char*)ws;
+    auto take = [&](size_t n) { double* r = (double*)p; p += n; return r; };
+    for (int i = 0; i < 9; ++i) w.th[i] = take(f2);
+    w.X = take(f6); w.A = take(f12); w.Bf = take(f12);
+    w.partial = take(al((size_t)C * nblk * 8));
+    w.logdet = take(al((size_t)C * 8));
+    w.sums_old = take(al((size_t)C * 3 * 8)); w.sums_new = take(al((size_t)C * 3 * 8));
+    w.H_old = take(al((size_t)C * 8)); w.H_new = take(al((size_t)C * 8));
+    w.acc = (int32_t*)take(al((size_t)C * 4));
+    w.th_new = take(f2); w.pi = take(f2); w.force = take(f2);
+    if (backward) {
+        for (int i = 0; i < 8; ++i) w.Kk[i] = take(f12);
+        w.D = take((size_t)8 * n_layers * f12);
+        w.AP = take(f1); w.AR = take(f1); w.PT = take(f1);
+        w.g0 = take(f2); w.g1 = take(f2);
+    } else {
+        for (int i = 0; i < 8; ++i) w.Kk[i] = w.A;   // unused
+        w.Kk[0] = take(f12);                          // single K buffer reused by every subset
+        for (int i = 1; i < 8; ++i) w.Kk[i] = w.Kk[0];
+    }
+    w.bytes = (size_t)(p - (char*)ws);
+    return w;
+}
+
+static inline double* Dbuf(const FtWs& w, int n_layers, int C, int L, int k, int layer) {
+    const size_t f12 = al((size_t)C * kW * (size_t)L * L * 8);
+    return (double*)((char*)w.D + ((size_t)k * n_layers + layer) * f12);
+}
+
+template <int CIN, int COUT, int EPI>
+static int launch_conv(const ConvP<CIN, COUT>& p, const double* in, const double* add, const double* mul,
+                       double* out, double* dout, int nsites, int L, cudaStream_t st) {
+    k_conv<CIN, COUT, EPI><<<blocks_for(nsites, kConvThreads), kConvThreads, 0, st>>>(p, in, add, mul, out, dout, nsites, L);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+// CNN forward of subset k on chunk of C chains: X -> K (w.Kk[k]).  store!=0 keeps GELU' for backward.
+static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool store, cudaStream_t st) {
+    const int ns = C * L * L, nl = h->n_layers;
+    auto D = [&](int layer) { return store ? Dbuf(w, nl, C, L, k, layer) : nullptr; };
+    const ConvP<kW, kW>* fk = &h->f[(size_t)k * (nl - 1)];
+    U1_TRY((launch_conv<kXC, kW, EPI_GELU>(h->f0[k], w.X, nullptr, nullptr, w.A, D(0), ns, L, st)));
+    for (int i = 0; i < h->n_res; ++i) {            // ResBlock (cnn_model_opt.py:74-87)
+        U1_TRY((launch_conv<kW, kW, EPI_GELU>(fk[2 * i], w.A, nullptr, nullptr, w.Bf, D(1 + 2 * i), ns, L, st)));
+        U1_TRY((launch_conv<kW, kW, EPI_GELU>(fk[2 * i + 1], w.Bf, w.A, nullptr, w.A, D(2 + 2 * i), ns, L, st)));
+    }
+    U1_TRY((launch_conv<kW, kW, EPI_FINAL>(fk[nl - 2], w.A, nullptr, nullptr, w.Kk[k], D(nl - 1), ns, L, st)));
+    return U1_OK;
+}
+
+// CNN reverse of subset k: zbar (in w.A) -> Xbar (w.X).
+static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cudaStream_t st) {
+    const int ns = C * L * L, nl = h->n_layers;
+    auto D = [&](int layer) { return Dbuf(w, nl, C, L, k, layer); };
+    const ConvP<kW, kW>* bk = &h->bt[(size_t)k * (nl - 1)];
+    // hbar = convT_final(zbar_f); times GELU' of the layer below
+    U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[nl - 2], w.A, nullptr, D(nl - 2), w.Bf, nullptr, ns, L, st)));
+    // now w.Bf = vbar of the last block (or zbar0 for `simple`)
+    double* cur = w.Bf;  double* oth = w.A;
+    for (int i = h->n_res - 1; i >= 0; --i) {
+        // z1bar = convT_2(vbar) * GELU'(conv1 pre-activation)
+        U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[2 * i + 1], cur, nullptr, D(1 + 2 * i), oth, nullptr, ns, L, st)));
+        // vbar_prev = (convT_1(z1bar) + vbar) * GELU'(layer below), in place over vbar
+        U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[2 * i], oth, cur, D(2 * i), cur, nullptr, ns, L, st)));
+    }
+    U1_TRY((launch_conv<kW, kXC, EPI_BWD>(h->b0[k], cur, nullptr, nullptr, w.X, nullptr, ns, L, st)));
+    return U1_OK;
+}
+
+// Forward sweep over the 8 subsets for a chunk: theta (w.th[0]) -> w.th[8], logdet.
+static int ft_forward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, bool store, bool want_logdet,
+                            cudaStream_t st) {
+    const int V = L * L, ns = C * V, nblk = blocks_for(V, kUpdThreads);
+    for (int k = 0; k < 8; ++k) {
+        k_ft_features<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[k], w.X, k, ns, L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        U1_TRY(cnn_forward(h, w, k, C, L, store, st));
+        k_ft_update<<<dim3(nblk, C), kUpdThreads, 0, st>>>(w.th[k], w.Kk[k], w.th[k + 1],
+                                                           want_logdet ? w.partial : nullptr, k, L, nblk, 0);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        if (want_logdet) {
+            k_ft_logdet_accum<<<blocks_for(C, 128), 128, 0, st>>>(w.partial, w.logdet, C, nblk, k == 0);
+            count_launch();
+            U1_CHECK_LAUNCH();
+        }
+    }
+    return U1_OK;
+}
+
+// S_ft (and sums of theta_ori) for the chunk already forwarded.
+static int ft_action_chunk(const FtWs& w, int C, int L, double beta, const double* pi, double* sums,
+                           double* S_ft, double* H, cudaStream_t st) {
+    k_chain_sums<<<C, 256, 0, st>>>(w.th[8], pi, sums, L);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_ft_hamiltonian<<<blocks_for(C, 128), 128, 0, st>>>(sums, w.logdet, S_ft, H, C, beta);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+// Reverse sweep: result (dS_FT/dtheta) lands in *result (one of w.g0/w.g1).
+static int ft_backward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double beta, double** result,
+                             cudaStream_t st) {
+    const int V = L * L, ns = C * V;
+    double* g = w.g0;  double* gn = w.g1;
+    k_plain_force<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[8], g, ns, L, beta);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    for (int k = 7; k >= 0; --k) {
+        cudaError_t e = cudaMemsetAsync(w.AP, 0, (size_t)C * V * 8, st);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(w.AR, 0, (size_t)C * V * 8, st);
+        if (e != cudaSuccess) return (int)e;
+        k_ft_update_bwd<<<blocks_for(ns, kUpdThreads), kUpdThreads, 0, st>>>(
+            w.th[k], w.Kk[k], Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1), g, w.A, w.AP, w.AR, k, ns, L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        U1_TRY(cnn_backward(h, w, k, C, L, st));
+        k_ft_feat_bwd<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[k], w.X, w.AP, w.AR, w.PT, k, ns, L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        k_ft_scatter<<<blocks_for(ns, 256), 256, 0, st>>>(g, w.PT, gn, ns, L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        double* t = g; g = gn; gn = t;
+    }
+    *result = g;
+    return U1_OK;
+}
+
+static int copy_async(void* dst, const void* src, size_t n, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st);
+    return e == cudaSuccess ? U1_OK : (int)e;
+}
+
+static int check_ws_ft(void* ws, size_t have, size_t need) {
+    if (!ws || have < need || (reinterpret_cast<uintptr_t>(ws) & 255u)) return U1_ERR_WORKSPACE;
+    return U1_OK;
+}
+
+// force for a chunk whose theta is in w.th[0]; result pointer returned; optional S_ft output.
+static int ft_force_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double beta, double* S_ft,
+                          double** result, cudaStream_t st) {
+    U1_TRY(ft_forward_chunk(h, w, C, L, true, true, st));
+    if (S_ft) U1_TRY(ft_action_chunk(w, C, L, beta, nullptr, w.sums_new, S_ft, nullptr, st));
+    return ft_backward_chunk(h, w, C, L, beta, result, st);
+}
+
+extern "C" {
+
+long long u1ft_set_chunk_sites(long long sites) {
+    const long long prev = chunk_sites();
+    g_chunk_sites.store(sites < 1 ? 1 : sites);
+    return prev;
+}
+
+size_t u1ft_weight_count(int n_res) {
+    if (n_res < 0 || n_res > 8) return 0;
+    const size_t first = (size_t)kW * kXC * 9 + kW, rest = (size_t)kW * kW * 9 + kW;
+    return 8 * (first + (size_t)(1 + 2 * n_res) * rest);
+}
+
+int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_doubles) {
+    if (!out || !weights) return U1_ERR_ARG;
+    if (n_res < 0 || n_res > 8 || n_doubles != u1ft_weight_count(n_res)) return U1_ERR_HANDLE;
+    u1ft_handle_s* h = new (std::nothrow) u1ft_handle_s();
+    if (!h) return U1_ERR_HANDLE;
+    h->magic = kMagic; h->n_res = n_res; h->n_layers = 2 + 2 * n_res;
+    const int nl = h->n_layers;
+    h->f0.resize(8); h->b0.resize(8); h->f.resize((size_t)8 * (nl - 1)); h->bt.resize((size_t)8 * (nl - 1));
+    const double* p = weights;
+    for (int s = 0; s < 8; ++s) {
+        for (int l = 0; l < nl; ++l) {
+            const int cin = (l == 0) ? kXC : kW;
+            const double* W = p;  p += (size_t)kW * cin * 9;      // W[o][c][tap]
+            const double* bias = p;  p += kW;
+            if (l == 0) {
+                for (int o = 0; o < kW; ++o) {
+                    h->f0[s].b[o] = bias[o];
+                    for (int c = 0; c < kXC; ++c)
+                        for (int t = 0; t < 9; ++t) {
+                            const double v = W[((size_t)o * kXC + c) * 9 + t];
+                            h->f0[s].w[(c * 9 + t) * kW + o] = v;
+                            h->b0[s].w[(o * 9 + (8 - t)) * kXC + c] = v;     // transposed + flipped
+                        }
+                }
+                for (int c = 0; c < kXC; ++c) h->b0[s].b[c] = 0.0;
+            } else {
+                ConvP<kW, kW>& F = h->f[(size_t)s * (nl - 1) + (l - 1)];
+                ConvP<kW, kW>& T = h->bt[(size_t)s * (nl - 1) + (l - 1)];
+                for (int o = 0; o < kW; ++o) {
+                    F.b[o] = bias[o];
+                    T.b[o] = 0.0;
+                    for (int c = 0; c < kW; ++c)
+                        for (int t = 0; t < 9; ++t) {
+                            const double v = W[((size_t)o * kW + c) * 9 + t];
+                            F.w[(c * 9 + t) * kW + o] = v;
+                            T.w[(o * 9 + (8 - t)) * kW + c] = v;
+                        }
+                }
+            }
+        }
+    }
+    *out = h;
+    return U1_OK;
+}
+
+int u1ft_destroy(u1ft_handle_t h) {
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    h->magic = 0;
+    delete h;
+    return U1_OK;
+}
+
+size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward) {
+    if (!handle_ok(h) || B <= 0 || L <= 0) return 0;
+    return carve_ft(nullptr, h->n_layers, chunk_chains(B, L), L, with_backward != 0).bytes;
+}
+
+int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
+                 int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || B <= 0 || L <= 0) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, false).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, false);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)2 * L * L;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        U1_TRY(copy_async(w.th[0], theta + (size_t)b0 * per, (size_t)C * per * 8, st));
+        U1_TRY(ft_forward_chunk(h, w, C, L, false, logdet != nullptr, st));
+        if (theta_ori) U1_TRY(copy_async(theta_ori + (size_t)b0 * per, w.th[8], (size_t)C * per * 8, st));
+        if (logdet) U1_TRY(copy_async(logdet + b0, w.logdet, (size_t)C * 8, st));
+    }
+    return U1_OK;
+}
+
+int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
+               int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || !delta || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, false).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, false);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = L * L, nblk = blocks_for(V, kUpdThreads);
+    const size_t per = (size_t)2 * V;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        const double* th = theta + (size_t)b0 * per;
+        k_ft_features<<<blocks_for((size_t)C * V, 256), 256, 0, st>>>(th, w.X, index, C * V, L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        U1_TRY(cnn_forward(h, w, index, C, L, false, st));
+        k_ft_update<<<dim3(nblk, C), kUpdThreads, 0, st>>>(th, w.Kk[index], delta + (size_t)b0 * per, nullptr,
+                                                           index, L, nblk, 1);
+        count_launch();
+        U1_CHECK_LAUNCH();
+    }
+    return U1_OK;
+}
+
+int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* theta_ori,
+                double* logdet, int B, int L, double beta,
+                void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || !S_ft || B <= 0 || L <= 0) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, false).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, false);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)2 * L * L;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        U1_TRY(copy_async(w.th[0], theta + (size_t)b0 * per, (size_t)C * per * 8, st));
+        U1_TRY(ft_forward_chunk(h, w, C, L, false, true, st));
+        U1_TRY(ft_action_chunk(w, C, L, beta, nullptr, w.sums_new, S_ft + b0, nullptr, st));
+        if (theta_ori) U1_TRY(copy_async(theta_ori + (size_t)b0 * per, w.th[8], (size_t)C * per * 8, st));
+        if (logdet) U1_TRY(copy_async(logdet + b0, w.logdet, (size_t)C * 8, st));
+    }
+    return U1_OK;
+}
+
+int u1ft_force(u1ft_handle_t h, const double* theta, double* force, double* S_ft,
+               int B, int L, double beta, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || !force || B <= 0 || L <= 0) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, true);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)2 * L * L;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        U1_TRY(copy_async(w.th[0], theta + (size_t)b0 * per, (size_t)C * per * 8, st));
+        double* res = nullptr;
+        U1_TRY(ft_force_chunk(h, w, C, L, beta, S_ft ? S_ft + b0 : nullptr, &res, st));
+        U1_TRY(copy_async(force + (size_t)b0 * per, res, (size_t)C * per * 8, st));
+    }
+    return U1_OK;
+}
+
+// leapfrog of one chunk: state in (w.th[0], w.pi), both updated in place (hmc_u1_ft.py:154-179).
+static int ft_leapfrog_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double beta, double dt,
+                             int n_steps, cudaStream_t st) {
+    const size_t n = (size_t)C * 2 * L * L;
+    for (int s = 0; s < n_steps; ++s) {
+        k_axpy<<<ew_grid_ft(n), 256, 0, st>>>(w.th[0], w.pi, s == 0 ? 0.5 * dt : dt, n);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        double* F = nullptr;
+        U1_TRY(ft_force_chunk(h, w, C, L, beta, nullptr, &F, st));
+        k_axpy<<<ew_grid_ft(n), 256, 0, st>>>(w.pi, F, -dt, n);
+        count_launch();
+        U1_CHECK_LAUNCH();
+    }
+    k_axpy_wrap<<<ew_grid_ft(n), 256, 0, st>>>(w.th[0], w.pi, 0.5 * dt, n);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1ft_leapfrog(u1ft_handle_t h, const double* theta_in, const double* pi_in,
+                  double* theta_out, double* pi_out, int B, int L, double beta, double dt,
+                  int n_steps, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || n_steps < 1) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, true);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)2 * L * L;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        U1_TRY(copy_async(w.th[0], theta_in + (size_t)b0 * per, (size_t)C * per * 8, st));
+        U1_TRY(copy_async(w.pi, pi_in + (size_t)b0 * per, (size_t)C * per * 8, st));
+        U1_TRY(ft_leapfrog_chunk(h, w, C, L, beta, dt, n_steps, st));
+        U1_TRY(copy_async(theta_out + (size_t)b0 * per, w.th[0], (size_t)C * per * 8, st));
+        U1_TRY(copy_async(pi_out + (size_t)b0 * per, w.pi, (size_t)C * per * 8, st));
+    }
+    return U1_OK;
+}
+
+int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, const double* u_inject,
+                    uint64_t seed, uint64_t chain0, uint64_t traj0, int n_traj,
+                    int B, int L, double beta, double dt, int n_steps,
+                    double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                    double* out_topo, double* theta_ori_out,
+                    void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, true);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = L * L;
+    const size_t per = (size_t)2 * V;
+    const double inv_vol = 1.0 / (double)V;
+    // chunk-outer, trajectory-inner: a chunk's state stays hot in L2 for the whole trajectory
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        const size_t n = (size_t)C * per;
+        double* th_cur = theta + (size_t)b0 * per;          // current (accepted) state, caller memory
+        for (int t = 0; t < n_traj; ++t) {
+            const uint64_t traj = traj0 + (uint64_t)t;
+            const size_t o = (size_t)t * B + b0;
+            // momenta (hmc_u1_ft.py:195)
+            if (pi_inject) U1_TRY(copy_async(w.pi, pi_inject + ((size_t)t * B + b0) * per, n * 8, st));
+            else {
+                k_momenta_ft<<<blocks_for((size_t)C * V, 256), 256, 0, st>>>(w.pi, seed, chain0 + b0, traj, C * V, V);
+                count_launch();
+                U1_CHECK_LAUNCH();
+            }
+            // H_old (hmc_u1_ft.py:196-197)
+            U1_TRY(copy_async(w.th[0], th_cur, n * 8, st));
+            U1_TRY(ft_forward_chunk(h, w, C, L, false, true, st));
+            U1_TRY(ft_action_chunk(w, C, L, beta, w.pi, w.sums_old, nullptr, w.H_old, st));
+            if (theta_ori_out && t == n_traj - 1)            // F(theta_old), kept if the step is rejected
+                U1_TRY(copy_async(theta_ori_out + (size_t)b0 * per, w.th[8], n * 8, st));
+            // leapfrog (hmc_u1_ft.py:199)
+            U1_TRY(ft_leapfrog_chunk(h, w, C, L, beta, dt, n_steps, st));
+            U1_TRY(copy_async(w.th_new, w.th[0], n * 8, st));
+            // H_new (hmc_u1_ft.py:200-201)
+            U1_TRY(ft_forward_chunk(h, w, C, L, false, true, st));
+            U1_TRY(ft_action_chunk(w, C, L, beta, w.pi, w.sums_new, nullptr, w.H_new, st));
+            k_ft_metropolis<<<blocks_for(C, 128), 128, 0, st>>>(
+                w.H_old, w.H_new, w.sums_old, w.sums_new, u_inject ? u_inject + o : nullptr, seed,
+                chain0 + b0, traj, C, inv_vol, out_dH ? out_dH + o : nullptr,
+                out_accept ? out_accept + o : nullptr, out_H ? out_H + o : nullptr,
+                out_plaq ? out_plaq + o : nullptr, out_topo ? out_topo + o : nullptr, w.acc);
+            count_launch();
+            U1_CHECK_LAUNCH();
+            k_select_chain<<<ew_grid_ft(n), 256, 0, st>>>(th_cur, w.th_new, w.acc, per, n);
+            count_launch();
+            U1_CHECK_LAUNCH();
+            if (theta_ori_out && t == n_traj - 1) {
+                k_select_chain<<<ew_grid_ft(n), 256, 0, st>>>(theta_ori_out + (size_t)b0 * per, w.th[8], w.acc, per, n);
+                count_launch();
+                U1_CHECK_LAUNCH();
+            }
+        }
+    }
+    return U1_OK;
+}
+
+}  // extern "C"

@@ -529,6 +529,23 @@ k_traj_resident(TrajArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_fp64_probe(double* __restrict__ out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    const double x = 1.0 - 1e-9, y = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
 static bool resident_supported(int L) { return L == 8 || L == 16 || L == 32 || L == 64; }
 
 template <int L, int TX, int TY>
@@ -619,6 +636,15 @@ int u1_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 long long u1_last_launch_count(void) { return g_launches; }
+
+int u1_fp64_probe(double* out, int blocks, int iters, u1_stream_t stream) {
+    g_launches = 0;
+    if (!out || blocks <= 0 || iters <= 0) return U1_ERR_ARG;
+    k_fp64_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
 
 int u1_plaquette(const double* theta, double* plaq, int B, int L, u1_stream_t stream) {
     g_launches = 0;

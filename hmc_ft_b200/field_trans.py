@@ -1,0 +1,207 @@
+"""FieldTransformation, inference half (2d_u1_cluster/field_trans_opt.py:26-398,654-692), on the
+sm_100a library.  Training (inverse / loss_fn / train*) is out of scope."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import WS, as_batch, check_field, require_cuda, stream_ptr, to_dev
+from .cnn_model import choose_cnn_model
+
+
+class FieldTransformation:
+    def __init__(self, lattice_size, device="cuda", n_subsets=8, if_check_jac=False, num_workers=0,
+                 identity_init=True, save_tag=None, model_tag="simple", fabric=None):
+        """Same signature as field_trans_opt.py:28 (fabric / num_workers are accepted and unused)."""
+        if n_subsets != 8:
+            raise ValueError("the checkerboard decomposition has exactly 8 subsets (utils.py:21-50)")
+        if lattice_size % 2:
+            raise ValueError("lattice_size must be even (utils.py:21-115 masks)")
+        self.L = int(lattice_size)
+        self.device = torch.device(device)
+        self.n_subsets = n_subsets
+        self.if_check_jac = if_check_jac
+        self.num_workers = num_workers
+        self.train_beta = None
+        self.model_tag = model_tag
+        self.save_tag = save_tag
+        self.fabric = fabric
+        self.print = print
+        self._lib = _lib.load()
+        self._dev = require_cuda(self.device if self.device.type == "cuda" else None)
+        cnn = choose_cnn_model(model_tag)
+        self.models = [cnn() for _ in range(n_subsets)]
+        if identity_init:                       # field_trans_opt.py:46-51
+            for m in self.models:
+                for p in m.parameters():
+                    torch.nn.init.normal_(p, mean=0.0, std=0.001)
+        self._handle: Optional[C.c_void_p] = None
+        self.gpu_launches = 0
+        self.sync_weights()
+
+    # ------------------------------------------------------------------ weights
+    def sync_weights(self) -> None:
+        """(Re)build the C handle from self.models (call after changing parameters)."""
+        blob = torch.cat([m.packed_weights() for m in self.models]).contiguous()
+        n_res = self.models[0].n_res_blocks
+        assert blob.numel() == self._lib.u1ft_weight_count(n_res)
+        h = C.c_void_p()
+        _lib.check(self._lib.u1ft_create(C.byref(h), n_res, blob.data_ptr(), blob.numel()), "u1ft_create")
+        self._release()
+        self._handle = h
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None and self._handle:
+            self._lib.u1ft_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _load_best_model(self, train_beta):
+        """field_trans_opt.py:654-692: CWD-relative checkpoint, per-subset state dicts, optional
+        'module.' prefix."""
+        tag = "" if self.save_tag is None else f"_{self.save_tag}"
+        path = f"models/best_model_opt_L{self.L}_train_beta{train_beta:.1f}{tag}.pt"
+        self.load_checkpoint(path)
+
+    def load_checkpoint(self, path: str) -> None:
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        for i, m in enumerate(self.models):
+            key = f"model_state_dict_{i}"
+            if key not in ck:
+                raise KeyError(f"State dict for model {i} not found in checkpoint")
+            sd = {k.replace("module.", ""): v for k, v in ck[key].items()}
+            m.load_state_dict(sd)
+        self.sync_weights()
+        if "epoch" in ck and "loss" in ck:
+            self.print(f"Loaded best models from epoch {ck['epoch'] + 1} with loss {ck['loss']:.6f}")
+
+    def load_weights_npz(self, path: str) -> None:
+        """Compact fixture format of this repo: keys 'arch', 's{subset}.{layer}.weight|bias'."""
+        z = np.load(path, allow_pickle=False)
+        if str(z["arch"]) != self.model_tag:
+            raise ValueError(f"{path} holds '{z['arch']}' weights, model_tag is '{self.model_tag}'")
+        for s, m in enumerate(self.models):
+            sd = {k[len(f"s{s}."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"s{s}.")}
+            m.load_state_dict(sd)
+        self.sync_weights()
+
+    # ------------------------------------------------------------------ helpers
+    def _stage(self, theta):
+        tb, single = as_batch(theta)
+        d = to_dev(tb, self._dev)
+        B, L = check_field(d)
+        if L != self.L:
+            raise ValueError(f"lattice size {L} != {self.L}")
+        return d, single, B
+
+    def _back(self, t, like, single=False):
+        if single:
+            t = t[0]
+        return t if like.device == t.device else t.to(like.device)
+
+    def workspace(self, B: int, backward: bool):
+        nb = self._lib.u1ft_workspace_bytes(self._handle, B, self.L, 1 if backward else 0)
+        return WS.get(self._dev, nb, "ft")
+
+    def _count(self):
+        self.gpu_launches += _lib.last_launch_count()
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, theta):
+        """field_trans_opt.py:219-235: [B,2,L,L] -> [B,2,L,L]."""
+        d, single, B = self._stage(theta)
+        out = torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_forward(self._handle, d.data_ptr(), out.data_ptr(), None, B, self.L, ws, nb,
+                                              stream_ptr(self._dev)), "u1ft_forward")
+        self._count()
+        return self._back(out, theta, single)
+
+    def field_transformation(self, theta):
+        """field_trans_opt.py:237-239 (single configuration [2,L,L])."""
+        return self.forward(theta)
+
+    def compute_jac_logdet(self, theta):
+        """field_trans_opt.py:284-383: [B,2,L,L] -> [B]."""
+        d, single, B = self._stage(theta)
+        out = torch.empty(B, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_forward(self._handle, d.data_ptr(), None, out.data_ptr(), B, self.L, ws, nb,
+                                              stream_ptr(self._dev)), "u1ft_forward")
+        self._count()
+        return self._back(out, theta)
+
+    def forward_and_logdet(self, theta):
+        d, single, B = self._stage(theta)
+        out = torch.empty_like(d)
+        ld = torch.empty(B, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_forward(self._handle, d.data_ptr(), out.data_ptr(), ld.data_ptr(), B, self.L,
+                                              ws, nb, stream_ptr(self._dev)), "u1ft_forward")
+        self._count()
+        return self._back(out, theta, single), self._back(ld, theta)
+
+    def ft_phase(self, theta, index):
+        """field_trans_opt.py:137-217."""
+        d, single, B = self._stage(theta)
+        out = torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_phase(self._handle, d.data_ptr(), int(index), out.data_ptr(), B, self.L, ws, nb,
+                                            stream_ptr(self._dev)), "u1ft_phase")
+        self._count()
+        return self._back(out, theta, single)
+
+    # torch.compile aliases of the reference (field_trans_opt.py:83-108)
+    forward_compiled = forward
+    field_transformation_compiled = field_transformation
+    compute_jac_logdet_compiled = compute_jac_logdet
+    ft_phase_compiled = ft_phase
+
+    def compute_action(self, theta, beta):
+        """field_trans_opt.py:392-398: -beta * sum cos(P) per chain."""
+        d, single, B = self._stage(theta)
+        out = torch.empty(B, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = WS.get(self._dev, self._lib.u1_workspace_bytes(B, self.L))
+            _lib.check(self._lib.u1_action(d.data_ptr(), out.data_ptr(), B, self.L, float(beta), ws, nb,
+                                           stream_ptr(self._dev)), "u1_action")
+        return self._back(out, theta)
+
+    compute_action_compiled = compute_action
+
+    # ------------------------------------------------------------------ HMC_U1_FT pieces
+    def new_action(self, theta, beta):
+        """hmc_u1_ft.py:101-125: S(F(theta)) - logdet, per chain (0-dim for [2,L,L])."""
+        d, single, B = self._stage(theta)
+        out = torch.empty(B, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_action(self._handle, d.data_ptr(), out.data_ptr(), None, None, B, self.L,
+                                             float(beta), ws, nb, stream_ptr(self._dev)), "u1ft_action")
+        self._count()
+        return self._back(out, theta, single)
+
+    def new_force(self, theta, beta):
+        """hmc_u1_ft.py:128-152 (hand-derived reverse pass on the device; no autograd)."""
+        d, single, B = self._stage(theta)
+        out = torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, True)
+            _lib.check(self._lib.u1ft_force(self._handle, d.data_ptr(), out.data_ptr(), None, B, self.L, float(beta),
+                                            ws, nb, stream_ptr(self._dev)), "u1ft_force")
+        self._count()
+        return self._back(out, theta, single)

@@ -89,6 +89,11 @@ int u1_trajectory(double* theta, const double* pi_inject, const double* u_inject
  * (bench.py reports it as gpu_launches). */
 long long u1_last_launch_count(void);
 
+/* FP64-FMA throughput probe (the roofline denominator of the FT path, which MEASURED_PEAKS.json
+ * does not hold): launches `blocks` CTAs of 256 threads, each thread issuing iters*32 dependent-
+ * chain-free DFMAs.  out: device [blocks*256] doubles (sink).  flops = blocks*256*iters*32*2. */
+int u1_fp64_probe(double* out, int blocks, int iters, u1_stream_t stream);
+
 /* ---------------- slab (domain-decomposed) variants for one large lattice ----------------
  * The lattice is split along x into slabs of Lx rows (global width L).  The caller supplies the
  * halo rows it received from its ring neighbours (NCCL send/recv through torch.distributed):
@@ -117,6 +122,10 @@ typedef struct u1ft_handle_s* u1ft_handle_t;
 int u1ft_create(u1ft_handle_t* out, int n_res_blocks, const double* weights, size_t n_doubles);
 int u1ft_destroy(u1ft_handle_t h);
 size_t u1ft_weight_count(int n_res_blocks);
+/* Tunable: lattice sites (chains x L^2) processed per kernel launch by the FT entry points, chosen
+ * so one layer's activations of a chunk stay in L2 (default 303104 = 74 chains at L=64; also
+ * settable through the environment variable U1FT_CHUNK_SITES).  Returns the previous value. */
+long long u1ft_set_chunk_sites(long long sites);
 /* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);
 /* field_trans_opt.py:219-243 forward / field_transformation and :284-383 compute_jac_logdet in
