@@ -4,6 +4,7 @@
 //
 // Reference semantics: 2d_u1_cluster/hmc_u1.py:56-97,219-225 and utils.py:118-196.
 #include "u1_common.cuh"
+#include "u1_fastmath.cuh"
 
 namespace u1 {
 
@@ -71,6 +72,22 @@ __global__ void k_momenta(double* __restrict__ pi, uint64_t seed, uint64_t chain
         philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, n0, n1);
         pi[(size_t)b * 2 * V + site] = n0;
         pi[(size_t)b * 2 * V + V + site] = n1;
+    }
+}
+
+__global__ void k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t chain, uint64_t traj,
+                               long long x_first, int Lx, int L, int Lxg) {
+    const long long n = (long long)Lx * L;
+    const PhiloxKey key = chain_key(seed, chain);
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
+         s += (long long)gridDim.x * blockDim.x) {
+        const int xl = (int)(s / L), y = (int)(s - (long long)xl * L);
+        long long xg = (x_first + xl) % Lxg;
+        if (xg < 0) xg += Lxg;
+        double n0, n1;
+        philox_site_normals(key, traj, (uint32_t)(xg * L + y), n0, n1);
+        pi[s] = n0;
+        pi[n + s] = n1;
     }
 }
 
@@ -176,7 +193,7 @@ __global__ void __launch_bounds__(kStepThreads) k_leapfrog_step(StepArgs a) {
     for (int i = tid; i < (TR + 1) * WS; i += kStepThreads) {
         const int r = i / WS, c = i - r * WS;       // already offset by +1 w.r.t. (-1,-1)
         const double p = t0[r * W + c] - t1[r * W + c] - t0[r * W + c + 1] + t1[(r + 1) * W + c];
-        sp[i] = sin(p);
+        sp[i] = fast_sin(p);
     }
     __syncthreads();
     // Phase 3: kick + write back.
@@ -472,7 +489,7 @@ k_traj_resident(TrajArgs a) {
 #pragma unroll
             for (int i = 0; i < TX; ++i)
 #pragma unroll
-                for (int j = 0; j < TY; ++j) S[i][j] = sin(S[i][j]);
+                for (int j = 0; j < TY; ++j) S[i][j] = fast_sin(S[i][j]);
 #pragma unroll
             for (int i = 0; i < TX; ++i) colB[(x0 + i) * NTY + ty] = S[i][TY - 1];
 #pragma unroll
@@ -742,6 +759,28 @@ int u1_leapfrog_step(const double* theta_in, const double* pi_in, double* theta_
     return launch_step(a, B, false, (cudaStream_t)stream);
 }
 
+int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                          int B, int Lx, int L, double beta, double drift, double kick,
+                          u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || Lx <= 0) return U1_ERR_ARG;
+    if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    StepArgs a{};
+    a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
+    a.Lx = Lx; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
+    return launch_step(a, B, false, (cudaStream_t)stream);
+}
+
+int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
+                    long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
+    g_launches = 0;
+    if (!pi || Lx <= 0 || L <= 0 || Lx_global <= 0) return U1_ERR_ARG;
+    k_momenta_rows<<<ew_grid((size_t)Lx * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, x_first, Lx, L, Lx_global);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
 // n_steps fused steps ping-ponging between (thA,piA) and (thB,piB); returns where the result is.
 static int leapfrog_stream(const double* th_in, const double* pi_in, PlainWs& w, int B, int L,
                            double beta, double dt, int n_steps, cudaStream_t st,
@@ -855,6 +894,42 @@ int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
     a.th_up = theta_up; a.pi_up = pi_up; a.th_dn = theta_dn; a.pi_dn = pi_dn;
     a.Lx = Lx; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
     return launch_step(a, 1, true, (cudaStream_t)stream);
+}
+
+int u1_drift_wrap(const double* theta, const double* pi, double* out, double a, size_t n,
+                  u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !pi || !out) return U1_ERR_ARG;
+    if (n == 0) return U1_OK;
+    k_final_drift<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(theta, pi, out, a, n);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_metropolis_sums(const double* sums_old, const double* sums_new, const double* u_inject,
+                       uint64_t seed, uint64_t chain0, uint64_t traj, int B, double beta, double volume,
+                       double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                       double* out_topo, u1_stream_t stream) {
+    g_launches = 0;
+    if (!sums_old || !sums_new || !out_accept || B <= 0 || !(volume > 0)) return U1_ERR_ARG;
+    k_metropolis<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        sums_old, sums_new, u_inject, seed, chain0, traj, B, beta, 1.0 / volume, out_dH, nullptr, out_H,
+        out_plaq, out_topo, out_accept);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_select_accepted(double* theta, const double* theta_new, const int32_t* accept,
+                       size_t per_chain, int B, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta || !theta_new || !accept || B <= 0 || per_chain == 0) return U1_ERR_ARG;
+    const size_t n = per_chain * (size_t)B;
+    k_select<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(theta, theta_new, accept, per_chain, n);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
 }
 
 int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, double* sums,

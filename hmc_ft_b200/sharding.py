@@ -1,0 +1,193 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+(i)  Chain sharding (BASELINE configs[1], [3]): independent chains are split over ranks; there is no
+     data-path collective — Philox streams are keyed by the GLOBAL chain id, so the ensemble is the
+     same for any GPU count; only per-chain observables are gathered.
+(ii) Domain decomposition of one large lattice (configs[4], L=4096): 1-D slabs along x.  Each rank
+     keeps an extended slab (own rows + k halo rows per side).  Halos of (theta, pi) are exchanged
+     with the two ring neighbours once every k leapfrog steps (NCCL send/recv over NVLink); between
+     exchanges the extended slab is advanced as a whole and the outer rows, which become stale one
+     row per step, are simply never used.  dH needs one 3-double all-reduce per Hamiltonian.
+     The reference has no such path; results are checked against the undecomposed chain.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._runtime import WS, require_cuda, stream_ptr
+
+
+# ----------------------------------------------------------------------------- chain sharding
+def shard_chains(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split of `total` chains: returns (global id of first local chain, local count).
+    Earlier ranks take the remainder, so counts differ by at most one."""
+    if not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(total, world)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def gather_chain_values(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """All-gather per-chain values ([..., B_local] on every rank) into [..., total], ordered by
+    global chain id.  Works for uneven shards (pads to the largest shard)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    counts = [shard_chains(total, world, r)[1] for r in range(world)]
+    mx = max(counts)
+    pad = torch.zeros(local.shape[:-1] + (mx,), dtype=local.dtype, device=local.device)
+    pad[..., : local.shape[-1]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous(), group=group)
+    return torch.cat([b[..., :c] for b, c in zip(bufs, counts)], dim=-1)
+
+
+# ----------------------------------------------------------------------------- halo exchange
+class HaloExchanger:
+    """Ring exchange of k boundary rows of an extended slab tensor ext[..., Lx + 2k, L]:
+    rows [k, 2k) go to the upper neighbour (rank-1) and become its bottom halo; rows [Lx, Lx+k)
+    go to the lower neighbour (rank+1) and become its top halo.  Backend-agnostic (nccl on the
+    GPUs, gloo in the CPU tests); world_size 1 degenerates to local periodic copies."""
+
+    def __init__(self, Lx: int, k: int, group=None):
+        self.Lx, self.k, self.group = Lx, k, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.up = (self.rank - 1) % self.world
+        self.dn = (self.rank + 1) % self.world
+        self.n_exchanges = 0
+        self.bytes_sent = 0
+
+    def exchange(self, ext: torch.Tensor) -> None:
+        k, Lx = self.k, self.Lx
+        first = ext[..., k:2 * k, :]                  # my first k own rows
+        last = ext[..., Lx:Lx + k, :]                 # my last k own rows
+        top, bot = ext[..., 0:k, :], ext[..., Lx + k:Lx + 2 * k, :]
+        self.n_exchanges += 1
+        if self.world == 1:
+            top.copy_(last)
+            bot.copy_(first)
+            return
+        s_up, s_dn = first.contiguous(), last.contiguous()
+        r_top, r_bot = torch.empty_like(s_dn), torch.empty_like(s_up)
+        # order matters when up == dn (world 2): the peer's sends arrive as (its first, its last)
+        ops = [dist.P2POp(dist.isend, s_up, self.up, self.group),
+               dist.P2POp(dist.isend, s_dn, self.dn, self.group),
+               dist.P2POp(dist.irecv, r_bot, self.dn, self.group),
+               dist.P2POp(dist.irecv, r_top, self.up, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        top.copy_(r_top)
+        bot.copy_(r_bot)
+        self.bytes_sent += (s_up.numel() + s_dn.numel()) * s_up.element_size()
+
+
+# ----------------------------------------------------------------------------- slab HMC
+class SlabHMC:
+    """Plain HMC (hmc_u1.py:82-97 semantics) of ONE L x L lattice decomposed into `world` slabs of
+    Lx = L/world rows.  Momenta are keyed by the global site index and the accept draw by
+    (seed, chain, traj) only, so every rank takes the same Metropolis decision and the chain is
+    identical (up to reduction round-off in dH) to the undecomposed one."""
+
+    def __init__(self, lattice_size: int, beta: float, n_steps: int, step_size: float, halo: int = 10,
+                 seed: int = 1331, chain: int = 0, group=None, device=None):
+        self.L, self.beta, self.n_steps, self.dt = int(lattice_size), float(beta), int(n_steps), float(step_size)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.L % self.world or self.L % 2:
+            raise ValueError("L must be even and divisible by the number of ranks")
+        self.Lx = self.L // self.world
+        self.k = max(1, min(int(halo), self.Lx, self.n_steps))
+        self.x0 = self.rank * self.Lx
+        self.seed, self.chain = int(seed), int(chain)
+        self.traj_counter = 0
+        self.gpu_launches = 0
+        self._lib = _lib.load()
+        self._dev = require_cuda(device)
+        self.halo = HaloExchanger(self.Lx, self.k, group)
+        Lxe = self.Lx + 2 * self.k
+        # ext[f][mu][row][y], f = 0 theta, 1 pi ; two buffers for the out-of-place step kernel
+        self._ext = [torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev) for _ in range(2)]
+        self._sums = torch.zeros(3, dtype=torch.float64, device=self._dev)
+
+    def initialize(self) -> torch.Tensor:
+        return torch.zeros(2, self.Lx, self.L, dtype=torch.float64, device=self._dev)
+
+    # -- pieces ---------------------------------------------------------------------------
+    def _call(self, status, what):
+        _lib.check(status, what)
+        self.gpu_launches += _lib.last_launch_count()
+
+    def _global_sums(self, theta_own: torch.Tensor, theta_dn_row: torch.Tensor, pi_own: Optional[torch.Tensor]):
+        """[sum cos wrapP, sum wrapP, sum pi^2] over the whole lattice (all-reduced)."""
+        with torch.cuda.device(self._dev):
+            ws, nb = WS.get(self._dev, 4096 + 24 * (self.Lx // 16 + 2), "slab")
+            self._call(self._lib.u1_slab_sums(theta_own.data_ptr(), theta_dn_row.data_ptr(),
+                                              None if pi_own is None else pi_own.data_ptr(), self._sums.data_ptr(),
+                                              self.Lx, self.L, ws, nb, stream_ptr(self._dev)), "u1_slab_sums")
+        out = self._sums.clone()
+        if self.world > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+    def trajectory(self, theta_own: torch.Tensor, u: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """One Metropolis step.  theta_own [2,Lx,L] (this rank's rows, contiguous fp64 on the device) is
+        updated in place.  Returns 1-element device tensors dH, accept, H, plaq, topo (no host sync)."""
+        L, Lx, k, dt = self.L, self.Lx, self.k, self.dt
+        lib, dev = self._lib, self._dev
+        traj = self.traj_counter
+        cur, nxt = self._ext
+        own = slice(k, k + Lx)
+        with torch.cuda.device(dev):
+            sp = stream_ptr(dev)
+            cur[0, :, own] = theta_own
+            # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
+            self._call(lib.u1_momenta_rows(cur[1].data_ptr(), self.seed, self.chain, traj, self.x0 - k,
+                                           Lx + 2 * k, L, L, sp), "u1_momenta_rows")
+            self.halo.exchange(cur[0])                      # theta halos
+            th_c = cur[0, :, own].contiguous()
+            pi_c = cur[1, :, own].contiguous()
+            dn_row = cur[0, :, k + Lx].contiguous()          # first row of the lower neighbour, [2][L]
+            s_old = self._global_sums(th_c, dn_row, pi_c)
+            fresh = k                                        # valid halo depth of `cur`
+            for s in range(self.n_steps):
+                if fresh == 0:
+                    self.halo.exchange(cur)                  # theta and pi, k rows each side
+                    fresh = k
+                drift = 0.5 * dt if s == 0 else dt
+                self._call(lib.u1_leapfrog_step_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
+                                                     nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta, drift, dt, sp),
+                           "u1_leapfrog_step_rect")
+                cur, nxt = nxt, cur
+                fresh -= 1
+            # final half drift + wrap on own rows (hmc_u1.py:78-79), then H_new
+            th_new = torch.empty(2, Lx, L, dtype=torch.float64, device=dev)
+            pi_c = cur[1, :, own].contiguous()
+            th_c = cur[0, :, own].contiguous()
+            self._call(lib.u1_drift_wrap(th_c.data_ptr(), pi_c.data_ptr(), th_new.data_ptr(), 0.5 * dt,
+                                         th_new.numel(), sp), "u1_drift_wrap")
+            cur[0, :, own] = th_new
+            self.halo.exchange(cur[0])
+            dn_row = cur[0, :, k + Lx].contiguous()
+            s_new = self._global_sums(th_new, dn_row, pi_c)
+            # every rank takes the same decision from the all-reduced sums and the shared Philox draw
+            out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
+            out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
+            u_d = None if u is None else torch.tensor([float(u)], dtype=torch.float64, device=dev)
+            self._call(lib.u1_metropolis_sums(s_old.data_ptr(), s_new.data_ptr(), None if u_d is None else u_d.data_ptr(),
+                                              self.seed, self.chain, traj, 1, self.beta, float(L) * L,
+                                              out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
+                                              out["plaq"].data_ptr(), out["topo"].data_ptr(), sp), "u1_metropolis_sums")
+            self._call(lib.u1_select_accepted(theta_own.data_ptr(), th_new.data_ptr(), out["accept"].data_ptr(),
+                                              theta_own.numel(), 1, sp), "u1_select_accepted")
+        self._ext = [cur, nxt]
+        self.traj_counter += 1
+        return out

@@ -108,6 +108,32 @@ int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
                           double* theta_out, double* pi_out,
                           int Lx, int L, double beta, double drift, double kick,
                           u1_stream_t stream);
+/* Communication-avoiding variant: the caller keeps an extended slab of Lx rows (own rows plus k
+ * halo rows on each side, refreshed every k steps) and advances it as a periodic Lx x L lattice;
+ * rows within s of the slab edge are invalid after s steps and are never read by the caller.
+ * Same kernel as u1_leapfrog_step with a rectangular lattice. */
+int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                          int B, int Lx, int L, double beta, double drift, double kick,
+                          u1_stream_t stream);
+/* Philox momenta for rows x_first .. x_first+Lx-1 (taken modulo Lx_global) of ONE global lattice of
+ * Lx_global x L sites: pi[2][Lx][L].  Keyed by the global site index, so the field does not depend
+ * on the decomposition. */
+int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
+                    long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream);
+/* out = regularize(theta + a*pi), elementwise over n doubles (last half drift, hmc_u1.py:78-79). */
+int u1_drift_wrap(const double* theta, const double* pi, double* out, double a, size_t n,
+                  u1_stream_t stream);
+/* Metropolis decision from Hamiltonian sums (hmc_u1.py:84-97): sums_* are [B][3] =
+ * {sum cos(wrap P), sum wrap P, sum pi^2}; H = -beta*s0 + s2/2; accept iff u < exp(-dH) with u
+ * injected ([B]) or drawn from Philox(seed, chain0+b, traj).  out_accept (int32 [B]) is required,
+ * the other outputs may be NULL.  plaq/topo are those of the state kept. */
+int u1_metropolis_sums(const double* sums_old, const double* sums_new, const double* u_inject,
+                       uint64_t seed, uint64_t chain0, uint64_t traj, int B, double beta, double volume,
+                       double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                       double* out_topo, u1_stream_t stream);
+/* theta[b] = theta_new[b] for every chain with accept[b] != 0 (per_chain doubles per chain). */
+int u1_select_accepted(double* theta, const double* theta_new, const int32_t* accept,
+                       size_t per_chain, int B, u1_stream_t stream);
 /* Partial sums of one slab: sums[0]=sum cos(wrap P), sums[1]=sum wrap P, sums[2]=sum pi^2
  * (pi may be NULL).  theta_dn as above (first row of the lower neighbour). */
 int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, double* sums,

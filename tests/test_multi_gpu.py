@@ -1,0 +1,27 @@
+"""Domain-decomposed plain HMC (BASELINE configs[4] path) against the undecomposed chain."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
+
+
+@pytest.mark.parametrize("L,halo", [(64, 1), (128, 3), (96, 8)])
+def test_slab_world1_matches_plain_chain(L, halo):
+    out = subprocess.run([sys.executable, WORKER, str(L), str(halo)], capture_output=True, text=True, timeout=600)
+    assert "SLAB_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_multi_gpu_matches_plain_chain(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", WORKER, "256", "4"],
+                         capture_output=True, text=True, timeout=900)
+    assert "SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
