@@ -279,6 +279,15 @@ def run_ours(args):
         except Exception as e:      # FT numbers are secondary to the contract line
             extra["ft"] = {"error": f"{type(e).__name__}: {e}"}
 
+    if not args.no_slab:
+        try:
+            from bench_ft import bench_slab
+            extra["slab"] = bench_slab(args, rank, world, dev, time_steps)
+            extra["slab"]["hbm_frac_of_measured_peak_per_gpu"] = (
+                extra["slab"]["value"] / world * BYTES_PER_SITE_UPDATE / 1e9 / peak)
+        except Exception as e:
+            extra["slab"] = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_baseline_plain()
@@ -307,6 +316,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-ft", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-slab", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -62,3 +62,22 @@ def bench_ft(args, rank, world, dev, time_steps, arch="rnet3", L=64, beta=6.0, n
                      "note": "algorithmic flops = convolution MACs only, 8 subsets x MAC x 2 x (2 n_steps + 3) "
                              "per site per trajectory (SURVEY §8d); per GPU"},
     }
+
+
+def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50, dt=0.06, halo=10, steps=3, warmup=2):
+    """BASELINE configs[4]: one L=4096 lattice, plain HMC, slab-decomposed over the ranks with a
+    k-row NVLink halo exchange every k steps (hmc_ft_b200/sharding.py SlabHMC)."""
+    from hmc_ft_b200.sharding import SlabHMC
+    slab = SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0)
+    g = torch.Generator().manual_seed(7 + rank)
+    own = ((torch.rand(2, slab.Lx, L, generator=g, dtype=torch.float64) * 2 - 1) * 0.5).to(dev)
+    outs = []
+    ms = time_steps(lambda: outs.append(slab.trajectory(own)), steps, warmup, world)
+    su = L * L * n_steps / (ms * 1e-3)
+    return {"metric": f"site-updates/s, single lattice L={L} plain HMC, slab-decomposed over {world} GPU(s), "
+                      f"halo {slab.k} rows exchanged every {slab.k} steps",
+            "value": su, "unit": "site-updates/s", "ms_per_step": ms, "scaling": "strong",
+            "rows_per_gpu": slab.Lx, "halo_exchanges_per_trajectory": slab.halo.n_exchanges // (steps + warmup),
+            "halo_bytes_sent_per_trajectory_per_gpu": slab.halo.bytes_sent // (steps + warmup),
+            "gpu_launches_per_step": slab.gpu_launches // (steps + warmup),
+            "hbm_frac_of_measured_peak_per_gpu": None}
