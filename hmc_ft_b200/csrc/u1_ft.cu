@@ -34,14 +34,57 @@ struct ConvP {
 
 enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
 
-// exact-erf GELU (nn.GELU default) and its derivative.
-__device__ __forceinline__ void gelu_and_grad(double z, double& a, double& d, bool want_d) {
-    const double cdf = 0.5 * (1.0 + erf(z * 0.70710678118654752440));
-    a = z * cdf;
-    d = want_d ? fma(z * 0.39894228040143267794, exp(-0.5 * z * z), cdf) : 0.0;
+// ---------------------------------------------------------------------------------------
+// exact-erf GELU (nn.GELU default, a = z*Phi(z)) and its derivative (Phi + z*phi) from a piecewise
+// Taylor table of Phi held in shared memory: 136 intervals of width 1/8 on [-8.5, 8.5], degree 11
+// (truncation < 2e-20 for Phi, < 4e-18 for phi = Phi'), evaluated by one Horner pass that carries
+// the derivative: 22 DFMA + 12 LDS per value instead of the ~135 instruction slots of
+// erf() + exp().  The table is built in 80-bit arithmetic at handle creation (build_gelu_table).
+// ---------------------------------------------------------------------------------------
+constexpr int kGeluIntervals = 136, kGeluDeg = 11, kGeluStride = 13;   // odd stride: conflict-free banks
+constexpr double kGeluZmax = 8.5, kGeluInvH = 8.0;
+constexpr int kGeluTableDoubles = kGeluIntervals * kGeluStride;
+
+__device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, double z, double& a, double& d) {
+    const double zc = fmin(fmax(z, -kGeluZmax), kGeluZmax - 1e-9);
+    const int i = __double2int_rd((zc + kGeluZmax) * kGeluInvH);
+    const double t = zc - (((double)i + 0.5) * (1.0 / kGeluInvH) - kGeluZmax);
+    const double* q = tab + i * kGeluStride;
+    double p = q[kGeluDeg], dp = 0.0;
+#pragma unroll
+    for (int k = kGeluDeg - 1; k >= 0; --k) {
+        dp = fma(dp, t, p);
+        p = fma(p, t, q[k]);
+    }
+    const bool lo = z < -kGeluZmax, hi = z > kGeluZmax;
+    p = lo ? 0.0 : (hi ? 1.0 : p);
+    dp = (lo || hi) ? 0.0 : dp;
+    a = z * p;
+    d = fma(z, dp, p);
+}
+
+static void build_gelu_table(double* out) {
+    const long double sqrt2pi = sqrtl(2.0L * acosl(-1.0L));
+    for (int i = 0; i < kGeluIntervals; ++i) {
+        const long double c = -(long double)kGeluZmax + ((long double)i + 0.5L) / (long double)kGeluInvH;
+        const long double phi = expl(-0.5L * c * c) / sqrt2pi;
+        long double he_prev = 0.0L, he = 1.0L;          // He_{-1} := 0, He_0 = 1
+        long double fact = 1.0L, sign = 1.0L;
+        out[i * kGeluStride + 0] = (double)(0.5L * erfcl(-c / sqrtl(2.0L)));
+        for (int k = 1; k <= kGeluDeg; ++k) {            // a_k = (-1)^(k-1) He_{k-1}(c) phi(c) / k!
+            fact *= (long double)k;
+            out[i * kGeluStride + k] = (double)(sign * he * phi / fact);
+            const long double he_next = c * he - (long double)(k - 1) * he_prev;
+            he_prev = he; he = he_next; sign = -sign;
+        }
+        for (int k = kGeluDeg + 1; k < kGeluStride; ++k) out[i * kGeluStride + k] = 0.0;
+    }
 }
 
 // out[o](x,y) = sum_{c,i,j} w[c][i*3+j][o] * in[c]((x+i-1)%L, (y+j-1)%L)   (+ epilogue)
+// One thread = two vertically adjacent sites (x, x+1; x even): a 4x3 window per input channel feeds
+// 2*9*COUT DFMAs; the channel loop stays rolled (constant-bank weights indexed by a uniform register)
+// so the body fits the instruction cache.
 //   EPI_GELU : z = acc + b (+ add);  out = GELU(z);  dout = GELU'(z)            (dout may be null)
 //   EPI_FINAL: z = acc + b;  y = GELU(z);  out = atan(y)/pi/2;  dout = GELU'(z)/((1+y^2) 2pi)
 //   EPI_BWD  : out = (acc (+ add)) (* mul)
@@ -49,52 +92,72 @@ template <int CIN, int COUT, int EPI>
 __global__ void __launch_bounds__(kConvThreads)
 k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
        const double* __restrict__ add, const double* __restrict__ mul,
-       double* __restrict__ out, double* __restrict__ dout, int nsites, int L) {
+       double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab,
+       int npairs, int L) {
+    extern __shared__ double s_tab[];
+    if (EPI != EPI_BWD) {
+        for (int i = threadIdx.x; i < kGeluTableDoubles; i += kConvThreads) s_tab[i] = gelu_tab[i];
+        __syncthreads();
+    }
     const int s = blockIdx.x * kConvThreads + threadIdx.x;
-    if (s >= nsites) return;
-    const int V = L * L;
-    const int b = s / V, r = s - b * V;
-    const int x = r / L, y = r - x * L;
-    const int xr[3] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x == L - 1 ? 0 : x + 1) * L};
+    if (s >= npairs) return;
+    const int V = L * L, HV = V >> 1;
+    const int b = s / HV, rp = s - b * HV;
+    const int xp = rp / L, y = rp - xp * L, x = 2 * xp;
+    const int xr[4] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x + 1) * L, (x + 2 >= L ? 0 : x + 2) * L};
     const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
     const double* ib = in + (size_t)b * CIN * V;
 
-    double acc[COUT];
+    double a0[COUT], a1[COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.0;
-#pragma unroll
+    for (int o = 0; o < COUT; ++o) { a0[o] = 0.0; a1[o] = 0.0; }
+#pragma unroll 1
     for (int c = 0; c < CIN; ++c) {
         const double* pc = ib + (size_t)c * V;
-        double v[9];
+        double v[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[xr[i] + yc[j]];
+        const double* w = p.w + c * 9 * COUT;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) v[i * 3 + j] = pc[xr[i] + yc[j]];
+            for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int o = 0; o < COUT; ++o) acc[o] = fma(p.w[(c * 9 + t) * COUT + o], v[t], acc[o]);
+                for (int o = 0; o < COUT; ++o) {
+                    const double wv = w[(i * 3 + j) * COUT + o];
+                    a0[o] = fma(wv, v[i][j], a0[o]);
+                    a1[o] = fma(wv, v[i + 1][j], a1[o]);
+                }
     }
-    const size_t ob = (size_t)b * COUT * V + r;
+    const size_t ob = (size_t)b * COUT * V + (size_t)x * L + y;
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
-        const size_t idx = ob + (size_t)o * V;
+        const size_t i0 = ob + (size_t)o * V, i1 = i0 + L;
         if (EPI == EPI_BWD) {
-            double rv = acc[o];
-            if (add) rv += add[idx];
-            if (mul) rv *= mul[idx];
-            out[idx] = rv;
+            double r0 = a0[o], r1 = a1[o];
+            if (add) { r0 += add[i0]; r1 += add[i1]; }
+            if (mul) { r0 *= mul[i0]; r1 *= mul[i1]; }
+            out[i0] = r0;
+            out[i1] = r1;
         } else {
-            double z = acc[o] + p.b[o];
-            if (EPI == EPI_GELU && add) z += add[idx];
-            double a, d;
-            gelu_and_grad(z, a, d, dout != nullptr);
+            double z0 = a0[o] + p.b[o], z1 = a1[o] + p.b[o];
+            if (EPI == EPI_GELU && add) { z0 += add[i0]; z1 += add[i1]; }
+            double g0, d0, g1, d1;
+            gelu_and_grad(s_tab, z0, g0, d0);
+            gelu_and_grad(s_tab, z1, g1, d1);
             if (EPI == EPI_GELU) {
-                out[idx] = a;
-                if (dout) dout[idx] = d;
+                out[i0] = g0;
+                out[i1] = g1;
+                if (dout) { dout[i0] = d0; dout[i1] = d1; }
             } else {
-                out[idx] = atan(a) / kPi / 2;                      // cnn_model_opt.py:46
-                if (dout) dout[idx] = d / ((1.0 + a * a) * kTwoPi);
+                out[i0] = atan(g0) / kPi / 2;                      // cnn_model_opt.py:46
+                out[i1] = atan(g1) / kPi / 2;
+                if (dout) {
+                    dout[i0] = d0 / ((1.0 + g0 * g0) * kTwoPi);
+                    dout[i1] = d1 / ((1.0 + g1 * g1) * kTwoPi);
+                }
             }
         }
     }
@@ -455,6 +518,8 @@ struct u1ft_handle_s {
     std::vector<ConvP<kW, kW>> f;                         // [8][n_layers-1]
     std::vector<ConvP<kW, kXC>> b0;                       // [8] transposed first layer (12->6)
     std::vector<ConvP<kW, kW>> bt;                        // [8][n_layers-1] transposed
+    double* gelu_tab;                                     // device copy of the GELU Taylor table
+    int device;
 };
 constexpr uint32_t kMagic = 0x55314654u;  // "U1FT"
 
@@ -466,12 +531,24 @@ static inline int ew_grid_ft(size_t n) {
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
+// Default chunk = the sites of ONE full wave of the widest kernel (k_conv 12->12 + GELU): every CTA
+// of a launch is resident at once (no partial second wave) and a layer's in/out activations of the
+// chunk (2 x 22 MB at L=64) stay in L2.
+static long long default_chunk_sites() {
+    int dev = 0, sms = 0, nb = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 227328;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 227328;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_conv<kW, kW, EPI_GELU>, kConvThreads,
+                                                      (size_t)kGeluTableDoubles * sizeof(double)) != cudaSuccess || nb < 1)
+        return 227328;
+    return (long long)sms * nb * kConvThreads * 2;
+}
 static std::atomic<long long> g_chunk_sites{-1};
 static long long chunk_sites() {
     long long t = g_chunk_sites.load();
     if (t < 0) {
         const char* e = getenv("U1FT_CHUNK_SITES");
-        t = e ? atoll(e) : 303104;            // 74 chains at L=64: 2368 CTAs of 128 = 2 waves of 148x8
+        t = e ? atoll(e) : default_chunk_sites();
         if (t < 1) t = 1;
         g_chunk_sites.store(t);
     }
@@ -537,9 +614,12 @@ static inline double* Dbuf(const FtWs& w, int n_layers, int C, int L, int k, int
 }
 
 template <int CIN, int COUT, int EPI>
-static int launch_conv(const ConvP<CIN, COUT>& p, const double* in, const double* add, const double* mul,
-                       double* out, double* dout, int nsites, int L, cudaStream_t st) {
-    k_conv<CIN, COUT, EPI><<<blocks_for(nsites, kConvThreads), kConvThreads, 0, st>>>(p, in, add, mul, out, dout, nsites, L);
+static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
+                       const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
+    const int npairs = nsites >> 1;
+    const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
+    k_conv<CIN, COUT, EPI><<<blocks_for(npairs, kConvThreads), kConvThreads, smem, st>>>(
+        p, in, add, mul, out, dout, h->gelu_tab, npairs, L);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
@@ -550,12 +630,12 @@ static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool
     const int ns = C * L * L, nl = h->n_layers;
     auto D = [&](int layer) { return store ? Dbuf(w, nl, C, L, k, layer) : nullptr; };
     const ConvP<kW, kW>* fk = &h->f[(size_t)k * (nl - 1)];
-    U1_TRY((launch_conv<kXC, kW, EPI_GELU>(h->f0[k], w.X, nullptr, nullptr, w.A, D(0), ns, L, st)));
+    U1_TRY((launch_conv<kXC, kW, EPI_GELU>(h, h->f0[k], w.X, nullptr, nullptr, w.A, D(0), ns, L, st)));
     for (int i = 0; i < h->n_res; ++i) {            // ResBlock (cnn_model_opt.py:74-87)
-        U1_TRY((launch_conv<kW, kW, EPI_GELU>(fk[2 * i], w.A, nullptr, nullptr, w.Bf, D(1 + 2 * i), ns, L, st)));
-        U1_TRY((launch_conv<kW, kW, EPI_GELU>(fk[2 * i + 1], w.Bf, w.A, nullptr, w.A, D(2 + 2 * i), ns, L, st)));
+        U1_TRY((launch_conv<kW, kW, EPI_GELU>(h, fk[2 * i], w.A, nullptr, nullptr, w.Bf, D(1 + 2 * i), ns, L, st)));
+        U1_TRY((launch_conv<kW, kW, EPI_GELU>(h, fk[2 * i + 1], w.Bf, w.A, nullptr, w.A, D(2 + 2 * i), ns, L, st)));
     }
-    U1_TRY((launch_conv<kW, kW, EPI_FINAL>(fk[nl - 2], w.A, nullptr, nullptr, w.Kk[k], D(nl - 1), ns, L, st)));
+    U1_TRY((launch_conv<kW, kW, EPI_FINAL>(h, fk[nl - 2], w.A, nullptr, nullptr, w.Kk[k], D(nl - 1), ns, L, st)));
     return U1_OK;
 }
 
@@ -565,16 +645,16 @@ static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cud
     auto D = [&](int layer) { return Dbuf(w, nl, C, L, k, layer); };
     const ConvP<kW, kW>* bk = &h->bt[(size_t)k * (nl - 1)];
     // hbar = convT_final(zbar_f); times GELU' of the layer below
-    U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[nl - 2], w.A, nullptr, D(nl - 2), w.Bf, nullptr, ns, L, st)));
+    U1_TRY((launch_conv<kW, kW, EPI_BWD>(h, bk[nl - 2], w.A, nullptr, D(nl - 2), w.Bf, nullptr, ns, L, st)));
     // now w.Bf = vbar of the last block (or zbar0 for `simple`)
     double* cur = w.Bf;  double* oth = w.A;
     for (int i = h->n_res - 1; i >= 0; --i) {
         // z1bar = convT_2(vbar) * GELU'(conv1 pre-activation)
-        U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[2 * i + 1], cur, nullptr, D(1 + 2 * i), oth, nullptr, ns, L, st)));
+        U1_TRY((launch_conv<kW, kW, EPI_BWD>(h, bk[2 * i + 1], cur, nullptr, D(1 + 2 * i), oth, nullptr, ns, L, st)));
         // vbar_prev = (convT_1(z1bar) + vbar) * GELU'(layer below), in place over vbar
-        U1_TRY((launch_conv<kW, kW, EPI_BWD>(bk[2 * i], oth, cur, D(2 * i), cur, nullptr, ns, L, st)));
+        U1_TRY((launch_conv<kW, kW, EPI_BWD>(h, bk[2 * i], oth, cur, D(2 * i), cur, nullptr, ns, L, st)));
     }
-    U1_TRY((launch_conv<kW, kXC, EPI_BWD>(h->b0[k], cur, nullptr, nullptr, w.X, nullptr, ns, L, st)));
+    U1_TRY((launch_conv<kW, kXC, EPI_BWD>(h, h->b0[k], cur, nullptr, nullptr, w.X, nullptr, ns, L, st)));
     return U1_OK;
 }
 
@@ -715,6 +795,18 @@ int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_d
             }
         }
     }
+    // GELU table: handle-private device memory on the current device
+    std::vector<double> tab(kGeluTableDoubles);
+    build_gelu_table(tab.data());
+    h->gelu_tab = nullptr;
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->gelu_tab, tab.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->gelu_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (h->gelu_tab) cudaFree(h->gelu_tab);
+        delete h;
+        return (int)e;
+    }
     *out = h;
     return U1_OK;
 }
@@ -722,6 +814,7 @@ int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_d
 int u1ft_destroy(u1ft_handle_t h) {
     if (!handle_ok(h)) return U1_ERR_HANDLE;
     h->magic = 0;
+    if (h->gelu_tab) cudaFree(h->gelu_tab);
     delete h;
     return U1_OK;
 }

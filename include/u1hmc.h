@@ -143,14 +143,16 @@ int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, 
 typedef struct u1ft_handle_s* u1ft_handle_t;
 /* field_trans_opt.py:654-692 (_load_best_model) + cnn_model_opt.py:6-247.
  * n_res_blocks: 0 = jointCNN_simple, 1 = jointCNN_rnet1, 3 = jointCNN_rnet3 (any 0..8 accepted).
+ * The handle owns a 14 KB device table (GELU Taylor coefficients) on the current device.
  * weights: HOST fp64 blob, for subset s=0..7, for each conv layer in forward order:
  *   W[o][c][3][3] (torch Conv2d layout) then b[o].  First layer 6->12, the rest 12->12. */
 int u1ft_create(u1ft_handle_t* out, int n_res_blocks, const double* weights, size_t n_doubles);
 int u1ft_destroy(u1ft_handle_t h);
 size_t u1ft_weight_count(int n_res_blocks);
 /* Tunable: lattice sites (chains x L^2) processed per kernel launch by the FT entry points, chosen
- * so one layer's activations of a chunk stay in L2 (default 303104 = 74 chains at L=64; also
- * settable through the environment variable U1FT_CHUNK_SITES).  Returns the previous value. */
+ * so one layer's activations of a chunk stay in L2 (default: one full wave of the 12->12 conv
+ * kernel, 227328 sites = 55 chains at L=64 on a 148-SM B200; also settable through the environment
+ * variable U1FT_CHUNK_SITES).  Returns the previous value. */
 long long u1ft_set_chunk_sites(long long sites);
 /* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);
