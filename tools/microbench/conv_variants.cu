@@ -1,0 +1,164 @@
+// Standalone microbenchmark of fp64 3x3 circular conv (12->12) inner-loop variants on B200.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/conv_variants tools/microbench/conv_variants.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <vector>
+#include <cmath>
+
+template <int CIN, int COUT> struct alignas(16) ConvP { double w[CIN * 9 * COUT]; double b[COUT]; };
+
+// ROWS vertically adjacent sites per thread, weights read as double2 (WV=2) or double (WV=1)
+template <int ROWS, int WV, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_conv(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
+    constexpr int CIN = 12, COUT = 12;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
+    if (s >= ngroups) return;
+    const int V = L * L, GV = V / ROWS;
+    const int b = s / GV, rp = s - b * GV;
+    const int xp = rp / L, y = rp - xp * L, x = ROWS * xp;
+    int xr[ROWS + 2];
+#pragma unroll
+    for (int i = 0; i < ROWS + 2; ++i) { int xx = x + i - 1; xx = xx < 0 ? xx + L : (xx >= L ? xx - L : xx); xr[i] = xx * L; }
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * CIN * V;
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < CIN; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[ROWS + 2][3];
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[xr[i] + yc[j]];
+        if (WV == 2) {
+            const double2* w2 = reinterpret_cast<const double2*>(p.w) + c * 9 * COUT / 2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int o = 0; o < COUT; o += 2) {
+                        const double2 wv = w2[((i * 3 + j) * COUT + o) / 2];
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) {
+                            acc[r][o] = fma(wv.x, v[i + r][j], acc[r][o]);
+                            acc[r][o + 1] = fma(wv.y, v[i + r][j], acc[r][o + 1]);
+                        }
+                    }
+        } else {
+            const double* w = p.w + c * 9 * COUT;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) {
+                        const double wv = w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
+                    }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
+}
+
+// weights staged in shared memory (LDS.128 broadcast), ROWS sites per thread
+template <int ROWS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_conv_smem(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
+    constexpr int CIN = 12, COUT = 12;
+    __shared__ double2 sw[CIN * 9 * COUT / 2];
+    for (int i = threadIdx.x; i < CIN * 9 * COUT / 2; i += THREADS) sw[i] = make_double2(p.w[2 * i], p.w[2 * i + 1]);
+    __syncthreads();
+    const int s = blockIdx.x * THREADS + threadIdx.x;
+    if (s >= ngroups) return;
+    const int V = L * L, GV = V / ROWS;
+    const int b = s / GV, rp = s - b * GV;
+    const int xp = rp / L, y = rp - xp * L, x = ROWS * xp;
+    int xr[ROWS + 2];
+#pragma unroll
+    for (int i = 0; i < ROWS + 2; ++i) { int xx = x + i - 1; xx = xx < 0 ? xx + L : (xx >= L ? xx - L : xx); xr[i] = xx * L; }
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * CIN * V;
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < CIN; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[ROWS + 2][3];
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[xr[i] + yc[j]];
+        const double2* w2 = sw + c * 9 * COUT / 2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int o = 0; o < COUT; o += 2) {
+                    const double2 wv = w2[((i * 3 + j) * COUT + o) / 2];
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+                        acc[r][o] = fma(wv.x, v[i + r][j], acc[r][o]);
+                        acc[r][o + 1] = fma(wv.y, v[i + r][j], acc[r][o + 1]);
+                    }
+                }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
+}
+
+template <typename F>
+float time_it(F f, int reps = 20) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) f();
+    cudaEventRecord(a);
+    for (int i = 0; i < reps; ++i) f();
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    return ms / reps;
+}
+
+int main(int argc, char** argv) {
+    const int L = 64, B = argc > 1 ? atoi(argv[1]) : 166, V = L * L;
+    const size_t n = (size_t)B * 12 * V;
+    double *in, *out, *out2;
+    cudaMalloc(&in, n * 8); cudaMalloc(&out, n * 8); cudaMalloc(&out2, n * 8);
+    std::vector<double> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = sin(0.001 * i);
+    cudaMemcpy(in, h.data(), n * 8, cudaMemcpyHostToDevice);
+    ConvP<12, 12> p;
+    for (int i = 0; i < 12 * 9 * 12; ++i) p.w[i] = cos(0.37 * i) * 0.1;
+    const double ideal_us = (double)B * V * 1296 / (148.0 * 64 * 1.9e9) * 1e6;
+    printf("B=%d sites=%d ideal(1.9GHz)=%.1f us\n", B, B * V, ideal_us);
+    auto report = [&](const char* name, float ms) { printf("%-34s %8.1f us  %5.1f%% of DFMA peak@1.9GHz\n", name, ms * 1e3, ideal_us / (ms * 1e3) * 100); };
+#define RUN(ROWS, WV, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv<ROWS, WV, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out, ng, L); }); \
+        report("rows" #ROWS " wv" #WV " t" #T " minb" #MB, ms); }
+#define RUNS(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_smem<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
+        report("SMEM rows" #ROWS " t" #T " minb" #MB, ms); }
+    RUN(1, 1, 128, 1) RUN(1, 2, 128, 1)
+    RUN(2, 1, 128, 1) RUN(2, 2, 128, 1) RUN(2, 2, 64, 1) RUN(2, 2, 256, 1) RUN(2, 2, 128, 6)
+    RUN(4, 1, 128, 1) RUN(4, 2, 128, 1) RUN(4, 2, 64, 1) RUN(4, 2, 128, 3)
+    RUNS(1, 128, 1) RUNS(2, 128, 1) RUNS(4, 128, 1) RUNS(2, 256, 1) RUNS(4, 64, 1)
+    // correctness cross-check between two variants
+    { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); ng = B * V / 4; k_conv_smem<4, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out2, ng, L); }
+    std::vector<double> a(n), b2(n);
+    cudaMemcpy(a.data(), out, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b2.data(), out2, n * 8, cudaMemcpyDeviceToHost);
+    double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs(a[i] - b2[i]));
+    printf("max diff between variants %.3e  (%s)\n", md, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
