@@ -70,6 +70,67 @@ k_conv(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, d
         for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
 }
 
+// software-pipelined: the window of channel c+1 is loaded while channel c is being accumulated
+template <int ROWS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_conv_pf(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
+    constexpr int CIN = 12, COUT = 12;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
+    if (s >= ngroups) return;
+    const int V = L * L, GV = V / ROWS;
+    const int b = s / GV, rp = s - b * GV;
+    const int xp = rp / L, y = rp - xp * L, x = ROWS * xp;
+    int off[ROWS + 2][3];
+    {
+        const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i) {
+            int xx = x + i - 1; xx = xx < 0 ? xx + L : (xx >= L ? xx - L : xx);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) off[i][j] = xx * L + yc[j];
+        }
+    }
+    const double* ib = in + (size_t)b * CIN * V;
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+    double va[ROWS + 2][3], vb[ROWS + 2][3];
+    auto load = [&](double (&v)[ROWS + 2][3], int c) {
+        const double* pc = ib + (size_t)c * V;
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[off[i][j]];
+    };
+    auto mac = [&](const double (&v)[ROWS + 2][3], int c) {
+        const double* w = p.w + c * 9 * COUT;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    const double wv = w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
+                }
+    };
+    load(va, 0);
+#pragma unroll 1
+    for (int c = 0; c < CIN; c += 2) {
+        load(vb, c + 1);
+        mac(va, c);
+        if (c + 2 < CIN) load(va, c + 2);
+        mac(vb, c + 1);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
+}
+
 // weights staged in shared memory (LDS.128 broadcast), ROWS sites per thread
 template <int ROWS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -153,9 +214,12 @@ int main(int argc, char** argv) {
     RUN(1, 1, 128, 1) RUN(1, 2, 128, 1)
     RUN(2, 1, 128, 1) RUN(2, 2, 128, 1) RUN(2, 2, 64, 1) RUN(2, 2, 256, 1) RUN(2, 2, 128, 6)
     RUN(4, 1, 128, 1) RUN(4, 2, 128, 1) RUN(4, 2, 64, 1) RUN(4, 2, 128, 3)
-    RUNS(1, 128, 1) RUNS(2, 128, 1) RUNS(4, 128, 1) RUNS(2, 256, 1) RUNS(4, 64, 1)
+#define RUNP(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_pf<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
+        report("PREFETCH rows" #ROWS " t" #T " minb" #MB, ms); }
+    RUNP(1, 128, 1) RUNP(2, 128, 1) RUNP(2, 128, 4) RUNP(2, 128, 5) RUNP(2, 64, 8) RUNP(4, 128, 1) RUNP(4, 128, 2) RUNP(4, 128, 3) RUNP(4, 64, 4) RUNP(4, 64, 6)
+    RUNS(2, 128, 1)
     // correctness cross-check between two variants
-    { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); ng = B * V / 4; k_conv_smem<4, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out2, ng, L); }
+    { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); ng = B * V / 4; k_conv_pf<4, 128, 3><<<(ng + 127) / 128, 128>>>(p, in, out2, ng, L); }
     std::vector<double> a(n), b2(n);
     cudaMemcpy(a.data(), out, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b2.data(), out2, n * 8, cudaMemcpyDeviceToHost);
     double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs(a[i] - b2[i]));
