@@ -211,11 +211,15 @@ int main(int argc, char** argv) {
         report("rows" #ROWS " wv" #WV " t" #T " minb" #MB, ms); }
 #define RUNS(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_smem<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
         report("SMEM rows" #ROWS " t" #T " minb" #MB, ms); }
+#define RUNP(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_pf<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
+        report("PREFETCH rows" #ROWS " t" #T " minb" #MB, ms); }
+    const int only = argc > 2 ? atoi(argv[2]) : -1;     // profile a single variant under ncu
+    if (only == 0) { RUN(2, 2, 128, 1) return 0; }
+    if (only == 1) { RUN(4, 2, 128, 3) return 0; }
+    if (only == 2) { RUNS(2, 128, 1) return 0; }
     RUN(1, 1, 128, 1) RUN(1, 2, 128, 1)
     RUN(2, 1, 128, 1) RUN(2, 2, 128, 1) RUN(2, 2, 64, 1) RUN(2, 2, 256, 1) RUN(2, 2, 128, 6)
     RUN(4, 1, 128, 1) RUN(4, 2, 128, 1) RUN(4, 2, 64, 1) RUN(4, 2, 128, 3)
-#define RUNP(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_pf<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
-        report("PREFETCH rows" #ROWS " t" #T " minb" #MB, ms); }
     RUNP(1, 128, 1) RUNP(2, 128, 1) RUNP(2, 128, 4) RUNP(2, 128, 5) RUNP(2, 64, 8) RUNP(4, 128, 1) RUNP(4, 128, 2) RUNP(4, 128, 3) RUNP(4, 64, 4) RUNP(4, 64, 6)
     RUNS(2, 128, 1)
     // correctness cross-check between two variants
