@@ -70,6 +70,54 @@ k_conv(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, d
         for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
 }
 
+// experiments: channel-loop unroll factor U; FAKE=1 no constant-bank weights, FAKE=2 no global loads in the loop
+template <int ROWS, int U, int FAKE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_conv_x(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
+    constexpr int CIN = 12, COUT = 12;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
+    if (s >= ngroups) return;
+    const int V = L * L, GV = V / ROWS;
+    const int b = s / GV, rp = s - b * GV;
+    const int xp = rp / L, y = rp - xp * L, x = ROWS * xp;
+    int xr[ROWS + 2];
+#pragma unroll
+    for (int i = 0; i < ROWS + 2; ++i) { int xx = x + i - 1; xx = xx < 0 ? xx + L : (xx >= L ? xx - L : xx); xr[i] = xx * L; }
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * CIN * V;
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+    double fw = in[s & 1023], fv = in[(s + 7) & 1023];
+#pragma unroll U
+    for (int c = 0; c < CIN; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[ROWS + 2][3];
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = (FAKE == 2) ? fv + (double)(i * 3 + j + c) : pc[xr[i] + yc[j]];
+        const double* w = p.w + c * 9 * COUT;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    const double wv = (FAKE == 1) ? fw : w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
+                }
+        if (FAKE == 1) fw += 1e-9;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
+}
+
 // software-pipelined: the window of channel c+1 is loaded while channel c is being accumulated
 template <int ROWS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -213,6 +261,15 @@ int main(int argc, char** argv) {
         report("SMEM rows" #ROWS " t" #T " minb" #MB, ms); }
 #define RUNP(ROWS, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_pf<ROWS, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
         report("PREFETCH rows" #ROWS " t" #T " minb" #MB, ms); }
+#define RUNX(ROWS, U, FAKE, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_x<ROWS, U, FAKE, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
+        report("X rows" #ROWS " unroll" #U " fake" #FAKE " t" #T " minb" #MB, ms); }
+    if (argc > 2 && atoi(argv[2]) == 9) {
+        RUNX(2, 1, 0, 128, 1) RUNX(2, 2, 0, 128, 1) RUNX(2, 3, 0, 128, 1) RUNX(2, 4, 0, 128, 1) RUNX(2, 6, 0, 128, 1) RUNX(2, 12, 0, 128, 1)
+        RUNX(2, 1, 1, 128, 1) RUNX(2, 1, 2, 128, 1) RUNX(2, 12, 1, 128, 1) RUNX(2, 12, 2, 128, 1)
+        RUNX(4, 1, 0, 128, 3) RUNX(4, 2, 0, 128, 3) RUNX(4, 3, 0, 128, 3) RUNX(4, 1, 1, 128, 3) RUNX(4, 1, 2, 128, 3)
+        RUNX(2, 2, 0, 128, 6) RUNX(2, 3, 0, 128, 6) RUNX(2, 4, 0, 128, 5) RUNX(2, 2, 0, 64, 10) RUNX(2, 2, 0, 256, 3)
+        return 0;
+    }
     const int only = argc > 2 ? atoi(argv[2]) : -1;     // profile a single variant under ncu
     if (only == 0) { RUN(2, 2, 128, 1) return 0; }
     if (only == 1) { RUN(4, 2, 128, 3) return 0; }
