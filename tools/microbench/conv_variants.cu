@@ -98,7 +98,7 @@ k_conv_x(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in,
 #pragma unroll
         for (int i = 0; i < ROWS + 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) v[i][j] = (FAKE == 2) ? fv + (double)(i * 3 + j + c) : pc[xr[i] + yc[j]];
+            for (int j = 0; j < 3; ++j) v[i][j] = (FAKE == 2 || FAKE >= 3) ? fv + (double)(i * 3 + j + c) : pc[xr[i] + yc[j]];
         const double* w = p.w + c * 9 * COUT;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -106,7 +106,7 @@ k_conv_x(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in,
             for (int j = 0; j < 3; ++j)
 #pragma unroll
                 for (int o = 0; o < COUT; ++o) {
-                    const double wv = (FAKE == 1) ? fw : w[(i * 3 + j) * COUT + o];
+                    const double wv = (FAKE == 1) ? fw : (FAKE >= 3 ? p.w[o + (FAKE == 4 ? 12 * j : 0)] : w[(i * 3 + j) * COUT + o]);
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
                 }
@@ -265,6 +265,10 @@ int main(int argc, char** argv) {
         report("X rows" #ROWS " unroll" #U " fake" #FAKE " t" #T " minb" #MB, ms); }
     if (argc > 2 && atoi(argv[2]) == 8) {
         RUNP(2, 128, 1) RUNP(2, 128, 4) RUNP(2, 128, 5) RUNP(2, 64, 8) RUNP(2, 256, 2) RUNP(4, 128, 1) RUNP(4, 128, 2) RUNP(4, 128, 3) RUNP(4, 64, 4) RUNP(4, 64, 6) RUNP(1, 128, 1) RUNP(1, 128, 8)
+        return 0;
+    }
+    if (argc > 2 && atoi(argv[2]) == 7) {
+        RUNX(2, 1, 2, 128, 1) RUNX(2, 1, 3, 128, 1) RUNX(2, 1, 4, 128, 1) RUNX(4, 1, 2, 128, 3) RUNX(4, 1, 3, 128, 3) RUNX(4, 1, 4, 128, 3)
         return 0;
     }
     if (argc > 2 && atoi(argv[2]) == 9) {
