@@ -133,6 +133,58 @@ class HMC_U1:
         self.traj_counter += n_traj
         return out
 
+    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices: int = 8):
+        """One Metropolis step of a HOST-resident batch [B,2,L,L] (fp64, ideally pinned): the batch is cut
+        into `n_slices` slices whose H2D copy, trajectory kernel and D2H copy run on rotating CUDA
+        streams, so the two PCIe directions and the SMs overlap.  Returns (theta_out_host, obs_host)
+        with obs_host = pinned fp64 [4,B] = (accept, H, plaq, topo).  Chains keep their global Philox
+        ids (chain_offset + index), so the result equals the resident path bit for bit."""
+        if theta_host.device.type != "cpu" or theta_host.dim() != 4 or theta_host.dtype != torch.float64:
+            raise ValueError("step_host expects a CPU fp64 tensor [B,2,L,L]")
+        B, L = check_field(theta_host)
+        dev = self._dev
+        if not theta_host.is_pinned():
+            theta_host = theta_host.pin_memory()
+        if out_host is None:
+            out_host = torch.empty_like(theta_host).pin_memory()
+        n_slices = max(1, min(n_slices, B))
+        key = (B, L, n_slices)
+        st = getattr(self, "_host_state", None)
+        if st is None or st["key"] != key:
+            st = {"key": key, "dev": torch.empty((B, 2, L, L), dtype=torch.float64, device=dev),
+                  "obs_d": torch.empty((4, B), dtype=torch.float64, device=dev),
+                  "obs_h": torch.empty((4, B), dtype=torch.float64).pin_memory(),
+                  "acc": torch.empty(B, dtype=torch.int32, device=dev),
+                  "streams": [torch.cuda.Stream(device=dev) for _ in range(min(3, n_slices))]}
+            self._host_state = st
+        cur = torch.cuda.current_stream(dev)
+        bounds = [(i * B) // n_slices for i in range(n_slices + 1)]
+        with torch.cuda.device(dev):
+            ws_all = [WS.get(dev, self._lib.u1_workspace_bytes(bounds[1] - bounds[0] + 1, L), f"host{j}")
+                      for j in range(len(st["streams"]))]
+            for i in range(n_slices):
+                a, b = bounds[i], bounds[i + 1]
+                s = st["streams"][i % len(st["streams"])]
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    d = st["dev"][a:b]
+                    d.copy_(theta_host[a:b], non_blocking=True)
+                    ws, nb = ws_all[i % len(st["streams"])]
+                    o = st["obs_d"]
+                    _lib.check(self._lib.u1_trajectory(
+                        d.data_ptr(), None, None, self.seed, self.chain_offset + a, self.traj_counter, 1,
+                        b - a, L, self.beta, self.dt, self.n_steps, None, st["acc"][a:b].data_ptr(),
+                        o[1, a:b].data_ptr(), o[2, a:b].data_ptr(), o[3, a:b].data_ptr(), self.kernel_path,
+                        ws, nb, s.cuda_stream), "u1_trajectory")
+                    self.gpu_launches += _lib.last_launch_count()
+                    o[0, a:b].copy_(st["acc"][a:b])
+                    out_host[a:b].copy_(d, non_blocking=True)
+                    st["obs_h"][:, a:b].copy_(o[:, a:b], non_blocking=True)
+            for s in st["streams"]:
+                cur.wait_stream(s)
+        self.traj_counter += 1
+        return out_host, st["obs_h"]
+
     def metropolis_step(self, theta, pi=None, u=None):
         """hmc_u1.py:82-97.  Single chain: (theta, bool, float) like the reference;
         batch: (theta [B,2,L,L], accepted bool[B], H[B])."""

@@ -176,3 +176,23 @@ def test_argument_errors(hb):
                              None, None, None, None, None, 2, None, 0, None) == -5
     assert lib.u1_trajectory(t.data_ptr(), None, None, 0, 0, 0, 1, 1, 12, 1.0, 0.1, 2,
                              None, None, None, None, None, 1, None, 0, None) == -3
+
+
+def test_step_host_pipeline_matches_resident(hb):
+    """Host-buffer step (sliced H2D / kernel / D2H over streams) == resident path, bit for bit."""
+    L, B, beta, n, dt = 32, 37, 3.0, 10, 0.1
+    g = torch.Generator().manual_seed(9)
+    th = (torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
+    h1 = hb.HMC_U1(L, beta, 0, n, dt, device="cuda", if_tune_step_size=False, n_chains=B, seed=5, chain_offset=3)
+    d = th.cuda().clone()
+    r = h1.trajectories(d, 1)
+    h2 = hb.HMC_U1(L, beta, 0, n, dt, device="cpu", if_tune_step_size=False, n_chains=B, seed=5, chain_offset=3)
+    out, obs = h2.step_host(th.clone(), n_slices=5)
+    torch.cuda.synchronize()
+    assert out.device.type == "cpu" and torch.equal(out, d.cpu())
+    assert torch.equal(obs[0], r["accept"][0].double().cpu()) and torch.equal(obs[1], r["H"][0].cpu())
+    assert torch.equal(obs[2], r["plaq"][0].cpu()) and torch.equal(obs[3], r["topo"][0].cpu())
+    out2, _ = h2.step_host(out, n_slices=1)       # second step continues the same Philox stream
+    r2 = h1.trajectories(d, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, d.cpu())
