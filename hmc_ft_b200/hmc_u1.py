@@ -179,9 +179,9 @@ class HMC_U1:
                     self.gpu_launches += _lib.last_launch_count()
                     o[0, a:b].copy_(st["acc"][a:b])
                     out_host[a:b].copy_(d, non_blocking=True)
-                    st["obs_h"][:, a:b].copy_(o[:, a:b], non_blocking=True)
             for s in st["streams"]:
                 cur.wait_stream(s)
+            st["obs_h"].copy_(st["obs_d"], non_blocking=True)      # one contiguous 4xB read-back
         self.traj_counter += 1
         return out_host, st["obs_h"]
 
