@@ -639,9 +639,10 @@ static inline int ew_grid_ft(size_t n) {
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
-// Default chunk = the sites of ONE full wave of the widest kernel (k_conv 12->12 + GELU): every CTA
-// of a launch is resident at once (no partial second wave) and a layer's in/out activations of the
-// chunk (2 x 22 MB at L=64) stay in L2.
+// Default chunk = the sites of EIGHT full waves of the widest kernel (k_conv 12->12 + GELU), i.e.
+// 444 chains at L=64: measured FT-force throughput grows with the chunk (15.5 TFLOP/s at one wave,
+// 20.1 at eight) because kernel-boundary ramps amortise; the convolutions are FP64-bound, so the
+// activations streaming through HBM (~290 B per site-layer) are hidden behind the math.
 static long long default_chunk_sites() {
     int dev = 0, sms = 0, nb = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 227328;
@@ -649,7 +650,7 @@ static long long default_chunk_sites() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_conv<kW, kW, EPI_GELU>, kConvThreads,
                                                       (size_t)kGeluTableDoubles * sizeof(double)) != cudaSuccess || nb < 1)
         return 227328;
-    return (long long)sms * nb * kConvThreads * 2;
+    return (long long)sms * nb * kConvThreads * 2 * 8;     // 8 waves: launch/ramp overheads amortised
 }
 static std::atomic<long long> g_chunk_sites{-1};
 static long long chunk_sites() {
@@ -666,8 +667,9 @@ static int chunk_chains(int B, int L) {
     const long long target = chunk_sites();
     long long c = target / ((long long)L * L);
     if (c < 1) c = 1;
-    if (c > B) c = B;
-    return (int)c;
+    if (c >= B) return B;
+    const long long nchunks = (B + c - 1) / c;              // balanced chunks: sizes differ by at most one chain
+    return (int)((B + nchunks - 1) / nchunks);
 }
 
 struct FtWs {

@@ -150,9 +150,9 @@ int u1ft_create(u1ft_handle_t* out, int n_res_blocks, const double* weights, siz
 int u1ft_destroy(u1ft_handle_t h);
 size_t u1ft_weight_count(int n_res_blocks);
 /* Tunable: lattice sites (chains x L^2) processed per kernel launch by the FT entry points, chosen
- * so one layer's activations of a chunk stay in L2 (default: one full wave of the 12->12 conv
- * kernel, 227328 sites = 55 chains at L=64 on a 148-SM B200; also settable through the environment
- * variable U1FT_CHUNK_SITES).  Returns the previous value. */
+ * (default: eight full waves of the 12->12 conv kernel, 1818624 sites = 444 chains at L=64 on a
+ * 148-SM B200; also settable through the environment variable U1FT_CHUNK_SITES).  Larger chunks
+ * amortise kernel-boundary ramps; the workspace grows linearly with it.  Returns the previous value. */
 long long u1ft_set_chunk_sites(long long sites);
 /* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);

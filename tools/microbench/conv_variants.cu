@@ -118,6 +118,71 @@ k_conv_x(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in,
         for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * L + y] = acc[r][o];
 }
 
+// TR x TC sites per thread (TC even, columns contiguous -> double2 loads), output channels processed in
+// NH passes of COUT/NH channels each (fewer live accumulators -> more sites per weight load).
+template <int TR, int TC, int NH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_conv_tile(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
+    constexpr int CIN = 12, COUT = 12, CH = COUT / NH;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
+    if (s >= ngroups) return;
+    const int V = L * L, GW = L / TC, GV = (L / TR) * GW;
+    const int b = s / GV, rp = s - b * GV;
+    const int xt = rp / GW, yt = rp - xt * GW;
+    const int x = xt * TR, y = yt * TC;
+    int xr[TR + 2];
+#pragma unroll
+    for (int i = 0; i < TR + 2; ++i) { int xx = x + i - 1; xx = xx < 0 ? xx + L : (xx >= L ? xx - L : xx); xr[i] = xx * L; }
+    const int ym = (y == 0 ? L - 1 : y - 1), yp = (y + TC >= L ? 0 : y + TC);
+    const double* ib = in + (size_t)b * CIN * V;
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+        double acc[TR][TC][CH];
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int q = 0; q < TC; ++q)
+#pragma unroll
+                for (int o = 0; o < CH; ++o) acc[r][q][o] = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < CIN; ++c) {
+            const double* pc = ib + (size_t)c * V;
+            double v[TR + 2][TC + 2];
+#pragma unroll
+            for (int i = 0; i < TR + 2; ++i) {
+                v[i][0] = pc[xr[i] + ym];
+#pragma unroll
+                for (int q = 0; q < TC; q += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(pc + xr[i] + y + q);
+                    v[i][1 + q] = t.x; v[i][2 + q] = t.y;
+                }
+                v[i][TC + 1] = pc[xr[i] + yp];
+            }
+            const double* w = p.w + c * 9 * COUT + h * CH;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int o = 0; o < CH; ++o) {
+                        const double wv = w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                        for (int r = 0; r < TR; ++r)
+#pragma unroll
+                            for (int q = 0; q < TC; ++q) acc[r][q][o] = fma(wv, v[i + r][j + q], acc[r][q][o]);
+                    }
+        }
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int o = 0; o < CH; ++o)
+#pragma unroll
+                for (int q = 0; q < TC; q += 2)
+                    *reinterpret_cast<double2*>(out + (size_t)b * COUT * V + (size_t)(h * CH + o) * V + (size_t)(x + r) * L + y + q) =
+                        make_double2(acc[r][q][o], acc[r][q + 1][o]);
+    }
+}
+
 // software-pipelined: the window of channel c+1 is loaded while channel c is being accumulated
 template <int ROWS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -265,6 +330,19 @@ int main(int argc, char** argv) {
         report("X rows" #ROWS " unroll" #U " fake" #FAKE " t" #T " minb" #MB, ms); }
     if (argc > 2 && atoi(argv[2]) == 8) {
         RUNP(2, 128, 1) RUNP(2, 128, 4) RUNP(2, 128, 5) RUNP(2, 64, 8) RUNP(2, 256, 2) RUNP(4, 128, 1) RUNP(4, 128, 2) RUNP(4, 128, 3) RUNP(4, 64, 4) RUNP(4, 64, 6) RUNP(1, 128, 1) RUNP(1, 128, 8)
+        return 0;
+    }
+#define RUNT(TR, TC, NH, T, MB) { int ng = B * V / (TR * TC); float ms = time_it([&] { k_conv_tile<TR, TC, NH, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
+        report("TILE " #TR "x" #TC " halves" #NH " t" #T " minb" #MB, ms); }
+    if (argc > 2 && atoi(argv[2]) == 6) {
+        RUNT(2, 2, 1, 128, 1) RUNT(2, 2, 1, 128, 3) RUNT(2, 2, 1, 64, 6) RUNT(1, 4, 1, 128, 3) RUNT(1, 2, 1, 128, 1)
+        RUNT(2, 4, 2, 128, 1) RUNT(2, 4, 2, 128, 2) RUNT(2, 4, 2, 128, 3) RUNT(2, 4, 2, 64, 4) RUNT(2, 4, 2, 64, 6)
+        RUNT(4, 2, 2, 128, 2) RUNT(4, 2, 2, 64, 4) RUNT(2, 2, 2, 128, 4) RUNT(2, 2, 2, 128, 6) RUNT(2, 4, 3, 128, 3) RUNT(2, 4, 4, 128, 4) RUNT(4, 4, 4, 128, 2) RUNT(4, 4, 4, 64, 4)
+        { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); ng = B * V / 8; k_conv_tile<2, 4, 2, 128, 2><<<(ng + 127) / 128, 128>>>(p, in, out2, ng, L); }
+        std::vector<double> a(n), b2(n);
+        cudaMemcpy(a.data(), out, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b2.data(), out2, n * 8, cudaMemcpyDeviceToHost);
+        double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs(a[i] - b2[i]));
+        printf("max diff tile vs rows2 %.3e (%s)\n", md, cudaGetErrorString(cudaGetLastError()));
         return 0;
     }
     if (argc > 2 && atoi(argv[2]) == 7) {
