@@ -5,6 +5,7 @@
 // Reference semantics: 2d_u1_cluster/hmc_u1.py:56-97,219-225 and utils.py:118-196.
 #include "u1_common.cuh"
 #include "u1_fastmath.cuh"
+#include <cstdlib>
 
 namespace u1 {
 
@@ -585,7 +586,7 @@ static int launch_resident(const TrajArgs& a, int L, cudaStream_t st) {
         case 8:  return launch_resident_t<8, 1, 2>(a, st);
         case 16: return launch_resident_t<16, 2, 4>(a, st);
         case 32: return launch_resident_t<32, 2, 4>(a, st);
-        case 64: return launch_resident_t<64, 2, 4>(a, st);
+        case 64: return (getenv("U1_RESIDENT_TX1") ? launch_resident_t<64, 1, 4>(a, st) : launch_resident_t<64, 2, 4>(a, st));
         default: return U1_ERR_UNSUPPORTED;
     }
 }
