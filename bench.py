@@ -233,7 +233,10 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (k_traj_resident): one launch == one step here ----
     ach = su_per_step * BYTES_PER_SITE_UPDATE / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "k_traj_resident<64,2,4>", "peak_source": peak_src,
+                "traffic": 273.1e6, "traffic_source": "ncu --set full, dram__bytes_read.sum+dram__bytes_write.sum per launch "
+                                                       "(profiles/r01_ncu_full_k_traj_resident_v2_fastsin.txt)",
+                "algorithmic_bytes_per_launch": su_per_step * BYTES_PER_SITE_UPDATE,
+                "kernel": "k_traj_resident<64,2,4>", "peak_source": peak_src,
                 "note": "algorithmic bytes = 64 B x site-updates (SURVEY §8d); the kernel keeps theta,pi in "
                         "registers for the whole trajectory so real DRAM traffic is ~n_steps x smaller: a frac "
                         "above 1 is expected; the binding unit is the FP64 pipe (see profiles/)"}
@@ -249,7 +252,9 @@ def run_ours(args):
     ms_k = time_steps(step_kernel, 20, 5, 1)
     ach_k = B * L * L * BYTES_PER_SITE_UPDATE / (ms_k * 1e-3) / 1e9
     roofline_stream = {"bound": "hbm", "achieved": ach_k, "peak": peak, "unit": "GB/s", "frac": ach_k / peak,
-                       "traffic": None, "kernel": "k_leapfrog_step<false>", "site_updates_per_s": B * L * L / (ms_k * 1e-3)}
+                       "traffic": 1028.7e6, "traffic_source": "ncu --set full (profiles/r01_ncu_full_k_leapfrog_step_v1.txt)",
+                       "algorithmic_bytes_per_launch": B * L * L * BYTES_PER_SITE_UPDATE,
+                       "kernel": "k_leapfrog_step<false>", "site_updates_per_s": B * L * L / (ms_k * 1e-3)}
 
     # ---- e2e: host buffers through the public class API, copies inside the timed region ----
     he = hb.HMC_U1(L, BETA, 0, N_STEPS, DT, device="cpu", if_tune_step_size=False, n_chains=B,
