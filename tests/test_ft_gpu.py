@@ -198,3 +198,19 @@ def test_ft_handle_errors():
     assert lib.u1ft_create(C.byref(h), 3, w.data_ptr(), 10) == -4
     assert lib.u1ft_weight_count(0) == 8 * 1968 and lib.u1ft_weight_count(1) == 8 * 4584 and lib.u1ft_weight_count(3) == 8 * 9816
     assert lib.u1ft_forward(None, None, None, None, 1, 8, None, 0, None) == -4
+
+
+def test_drivers_smoke(golden_dir, tmp_path):
+    """Thin CLI callers (compare_hmc.py / compare_fthmc.py / conf_gen.py flag surface)."""
+    from hmc_ft_b200.drivers import compare_fthmc, compare_hmc, conf_gen
+    plaq, acc, topo = compare_hmc.main(["--lattice_size", "16", "--n_configs", "8", "--beta", "2.0", "--step_size", "0.1",
+                                        "--max_lag", "4", "--no_tune", "--n_chains", "4"])
+    assert plaq.shape == (8, 4) and topo.shape == (8, 4)
+    plaq, acc, topo = compare_fthmc.main(["--lattice_size", "8", "--n_configs", "3", "--beta", "3.0", "--ft_step_size", "0.1",
+                                          "--max_lag", "2", "--model_tag", "simple", "--n_therm", "2",
+                                          "--weights", os.path.join(golden_dir, "weights_simple_beta6.0.npz")])
+    assert len(plaq) == 3
+    out = conf_gen.main(["--lattice_size", "8", "--n_configs", "6", "--beta", "2.0", "--n_chains", "3",
+                         "--out", str(tmp_path / "cfg.npy")])
+    a = np.load(out)
+    assert a.shape == (6, 2, 8, 8) and a.dtype == np.float32 and np.abs(a).max() <= math.pi + 1e-6
