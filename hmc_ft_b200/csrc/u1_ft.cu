@@ -89,7 +89,7 @@ static void build_gelu_table(double* out) {
 //   EPI_FINAL: z = acc + b;  y = GELU(z);  out = atan(y)/pi/2;  dout = GELU'(z)/((1+y^2) 2pi)
 //   EPI_BWD  : out = (acc (+ add)) (* mul)
 template <int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, EPI == EPI_BWD ? 6 : 5)
+__global__ void __launch_bounds__(kConvThreads)
 k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
        const double* __restrict__ add, const double* __restrict__ mul,
        double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab,
@@ -103,13 +103,9 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
         __syncthreads();
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // Persistent CTAs: the grid is one resident wave; CTA g owns the contiguous pair range
-    // [g*n/G, (g+1)*n/G).  Every SM gets the same amount of work whatever the batch size (no partial
-    // last wave); the ragged last pass inside a CTA costs little because one warp's 24 independent
-    // accumulators keep the FP64 pipe busy on their own.
+    const int s = blockIdx.x * kConvThreads + threadIdx.x;
+    if (s >= npairs) return;
     const int V = L * L, HV = V >> 1;
-    const int s_end = (int)(((long long)(blockIdx.x + 1) * npairs) / gridDim.x);
-    for (int s = (int)(((long long)blockIdx.x * npairs) / gridDim.x) + threadIdx.x; s < s_end; s += kConvThreads) {
     const int b = s / HV, rp = s - b * HV;
     const int xp = rp / L, y = rp - xp * L, x = 2 * xp;
     const int xr[4] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x + 1) * L, (x + 2 >= L ? 0 : x + 2) * L};
@@ -169,7 +165,6 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
             }
         }
     }
-    }   // pair loop
 }
 
 // ---------------------------------------------------------------------------------------
@@ -733,17 +728,8 @@ static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double*
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
     const int npairs = nsites >> 1;
     const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
-    static int wave = 0;        // resident CTAs of this instantiation on the current device (per template instance)
-    if (wave == 0) {
-        int dev = 0, sms = 148, nb = 4;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_conv<CIN, COUT, EPI>, kConvThreads, smem) != cudaSuccess || nb < 1) nb = 4;
-        wave = sms * nb;
-    }
-    const int want = blocks_for(npairs, kConvThreads);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(want < wave ? want : wave);
+    cfg.gridDim = dim3(blocks_for(npairs, kConvThreads));
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
