@@ -618,6 +618,8 @@ using namespace u1;
 // ---------------------------------------------------------------------------------------
 // Host side: handle, workspace carving, orchestration
 // ---------------------------------------------------------------------------------------
+constexpr int kLanes = 2;      // internal streams of u1ft_trajectory
+
 struct u1ft_handle_s {
     uint32_t magic;
     int n_res, n_layers;                                  // n_layers = 2 + 2*n_res
@@ -628,7 +630,22 @@ struct u1ft_handle_s {
     std::vector<ConvP<kW, kActCh>> fs;                    // [8] final layer, 6 active output channels of subset k
     double* gelu_tab;                                     // device copy of the GELU Taylor table
     int device;
+    cudaStream_t lane[kLanes];                            // internal streams of u1ft_trajectory (lazy)
+    cudaEvent_t ev_fork, ev_join[kLanes];
+    bool lanes_ready;
 };
+
+static int ensure_lanes(u1ft_handle_s* h) {
+    if (h->lanes_ready) return U1_OK;
+    cudaError_t e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (int l = 0; l < kLanes && e == cudaSuccess; ++l) {
+        e = cudaStreamCreateWithFlags(&h->lane[l], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return (int)e;
+    h->lanes_ready = true;
+    return U1_OK;
+}
 constexpr uint32_t kMagic = 0x55314654u;  // "U1FT"
 
 static inline bool handle_ok(u1ft_handle_t h) { return h && h->magic == kMagic; }
@@ -663,12 +680,18 @@ static long long chunk_sites() {
     }
     return t;
 }
+// Chunks are independent, so the trajectory entry point runs them on two internal streams ("lanes"):
+// while one lane's kernel drains (partial last wave, launch gap) the other lane's kernel fills the
+// idle SMs.  The number of chunks is a multiple of the lane count; sizes differ by at most one chain.
+static int lanes_for(int B) { return B >= 2 ? kLanes : 1; }
 static int chunk_chains(int B, int L) {
     const long long target = chunk_sites();
     long long c = target / ((long long)L * L);
     if (c < 1) c = 1;
-    if (c >= B) return B;
-    const long long nchunks = (B + c - 1) / c;              // balanced chunks: sizes differ by at most one chain
+    const int nl = lanes_for(B);
+    long long nchunks = (B + c - 1) / c;
+    if (nchunks < nl) nchunks = nl;
+    if (nchunks % nl) nchunks += nl - nchunks % nl;
     return (int)((B + nchunks - 1) / nchunks);
 }
 
@@ -916,6 +939,7 @@ int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_d
     u1ft_handle_s* h = new (std::nothrow) u1ft_handle_s();
     if (!h) return U1_ERR_HANDLE;
     h->magic = kMagic; h->n_res = n_res; h->n_layers = 2 + 2 * n_res;
+    h->lanes_ready = false;
     const int nl = h->n_layers;
     h->fs.resize(8);
     h->f0.resize(8); h->b0.resize(8); h->f.resize((size_t)8 * (nl - 1)); h->bt.resize((size_t)8 * (nl - 1));
@@ -982,13 +1006,17 @@ int u1ft_destroy(u1ft_handle_t h) {
     if (!handle_ok(h)) return U1_ERR_HANDLE;
     h->magic = 0;
     if (h->gelu_tab) cudaFree(h->gelu_tab);
+    if (h->lanes_ready) {
+        cudaEventDestroy(h->ev_fork);
+        for (int l = 0; l < kLanes; ++l) { cudaStreamDestroy(h->lane[l]); cudaEventDestroy(h->ev_join[l]); }
+    }
     delete h;
     return U1_OK;
 }
 
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward) {
     if (!handle_ok(h) || B <= 0 || L <= 0) return 0;
-    return carve_ft(nullptr, h->n_layers, chunk_chains(B, L), L, with_backward != 0).bytes;
+    return (size_t)lanes_for(B) * carve_ft(nullptr, h->n_layers, chunk_chains(B, L), L, with_backward != 0).bytes;
 }
 
 int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
@@ -1137,15 +1165,30 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
     if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
-    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes));
-    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, true);
-    cudaStream_t st = (cudaStream_t)stream;
+    const int nlanes = lanes_for(B);
+    const size_t lane_bytes = carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes;
+    U1_TRY(check_ws_ft(ws, ws_bytes, (size_t)nlanes * lane_bytes));
+    cudaStream_t user = (cudaStream_t)stream;
+    cudaStream_t lane_st[kLanes] = {user, user};
+    if (nlanes > 1) {                                   // fork: lanes start after everything queued on `stream`
+        U1_TRY(ensure_lanes(h));
+        cudaError_t e = cudaEventRecord(h->ev_fork, user);
+        for (int l = 0; l < nlanes && e == cudaSuccess; ++l) {
+            lane_st[l] = h->lane[l];
+            e = cudaStreamWaitEvent(h->lane[l], h->ev_fork, 0);
+        }
+        if (e != cudaSuccess) return (int)e;
+    }
     const int V = L * L;
     const size_t per = (size_t)2 * V;
     const double inv_vol = 1.0 / (double)V;
-    // chunk-outer, trajectory-inner: a chunk's state stays hot in L2 for the whole trajectory
-    for (int b0 = 0; b0 < B; b0 += Cmax) {
+    // chunk-outer, trajectory-inner; chunk i runs on lane i % nlanes with that lane's workspace
+    int chunk_idx = 0;
+    for (int b0 = 0; b0 < B; b0 += Cmax, ++chunk_idx) {
         const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        const int ln = chunk_idx % nlanes;
+        cudaStream_t st = lane_st[ln];
+        FtWs w = carve_ft((char*)ws + (size_t)ln * lane_bytes, h->n_layers, Cmax, L, true);
         const size_t n = (size_t)C * per;
         double* th_cur = theta + (size_t)b0 * per;          // current (accepted) state, caller memory
         for (int t = 0; t < n_traj; ++t) {
@@ -1185,6 +1228,13 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
                 count_launch();
                 U1_CHECK_LAUNCH();
             }
+        }
+    }
+    if (nlanes > 1) {                                   // join: `stream` continues after both lanes
+        for (int l = 0; l < nlanes; ++l) {
+            cudaError_t e = cudaEventRecord(h->ev_join[l], h->lane[l]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, h->ev_join[l], 0);
+            if (e != cudaSuccess) return (int)e;
         }
     }
     return U1_OK;
