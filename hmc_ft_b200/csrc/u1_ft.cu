@@ -683,7 +683,16 @@ static long long chunk_sites() {
 // Chunks are independent, so the trajectory entry point runs them on two internal streams ("lanes"):
 // while one lane's kernel drains (partial last wave, launch gap) the other lane's kernel fills the
 // idle SMs.  The number of chunks is a multiple of the lane count; sizes differ by at most one chain.
-static int lanes_for(int B) { return B >= 2 ? kLanes : 1; }
+static int lanes_for(int B) {
+    static int max_lanes = -1;
+    if (max_lanes < 0) {
+        const char* e = getenv("U1FT_LANES");
+        max_lanes = e ? atoi(e) : kLanes;
+        if (max_lanes < 1) max_lanes = 1;
+        if (max_lanes > kLanes) max_lanes = kLanes;
+    }
+    return B >= 2 ? max_lanes : 1;
+}
 static int chunk_chains(int B, int L) {
     const long long target = chunk_sites();
     long long c = target / ((long long)L * L);
