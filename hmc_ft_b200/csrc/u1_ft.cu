@@ -680,14 +680,15 @@ static long long chunk_sites() {
     }
     return t;
 }
-// Chunks are independent, so the trajectory entry point runs them on two internal streams ("lanes"):
-// while one lane's kernel drains (partial last wave, launch gap) the other lane's kernel fills the
-// idle SMs.  The number of chunks is a multiple of the lane count; sizes differ by at most one chain.
+// Chunks are independent, so the trajectory entry point CAN run them on two internal streams ("lanes",
+// U1FT_LANES=2) so that one lane's kernel fills the SMs another lane's kernel leaves idle while it
+// drains.  Off by default: with ~190 launches of 10 KB parameters per force the host launch rate
+// (~6 us per launch) becomes the limit once the per-lane kernels get short.
 static int lanes_for(int B) {
     static int max_lanes = -1;
     if (max_lanes < 0) {
         const char* e = getenv("U1FT_LANES");
-        max_lanes = e ? atoi(e) : kLanes;
+        max_lanes = e ? atoi(e) : 1;     // measured: 2 lanes are host-launch-bound below ~256 chains (18.7 -> 16.4 TFLOP/s at 128)
         if (max_lanes < 1) max_lanes = 1;
         if (max_lanes > kLanes) max_lanes = kLanes;
     }
