@@ -214,3 +214,48 @@ def test_drivers_smoke(golden_dir, tmp_path):
                          "--out", str(tmp_path / "cfg.npy")])
     a = np.load(out)
     assert a.shape == (6, 2, 8, 8) and a.dtype == np.float32 and np.abs(a).max() <= math.pi + 1e-6
+
+
+def test_ft_small_lattice_and_nan(golden_dir):
+    """L=4 (3x3 stencils wrap heavily) against the oracle; NaN input -> NaN dH -> reject."""
+    import hmc_ft_b200 as hb
+    L, B, beta = 4, 3, 2.0
+    wfile = "weights_rnet1_beta6.0.npz"
+    ft = make_ft(golden_dir, L, wfile)
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    fo = O.FieldTransformationOracle(L, nets)
+    g = torch.Generator().manual_seed(44)
+    th = (torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
+    assert rel(ft.new_force(th.cuda(), beta), fo.new_force(th, beta)) < 1e-12
+    assert rel(ft.compute_jac_logdet(th.cuda()), fo.compute_jac_logdet(th)) < 1e-12
+    h = hb.HMC_U1_FT(L, beta, 0, 3, 0.1, ft.field_transformation, ft.compute_jac_logdet, n_chains=B, if_tune_step_size=False)
+    d = th.cuda().clone()
+    d[2, 1, 0, 0] = float("nan")
+    keep = d.clone()
+    r = h.trajectories(d, 1)
+    assert r["accept"][0, 2].item() == 0 and torch.isnan(r["dH"][0, 2])
+    assert torch.equal(torch.nan_to_num(d[2], nan=5.0), torch.nan_to_num(keep[2], nan=5.0))
+    assert not torch.isnan(r["dH"][0, 0])
+
+
+def test_fthmc_matches_plain_hmc_ensemble(golden_dir):
+    """Matched runs: FT-HMC and plain HMC sample the same distribution — <plaq> and <Q^2>/V agree
+    within statistical error (L=16, beta=3, 512 chains each)."""
+    import hmc_ft_b200 as hb
+    L, beta, B = 16, 3.0, 512
+    ft = make_ft(golden_dir, L, "weights_rnet3_beta3.0.npz")
+    hf = hb.HMC_U1_FT(L, beta, 0, 10, 0.1, ft.field_transformation, ft.compute_jac_logdet, n_chains=B,
+                      if_tune_step_size=False, seed=11)
+    hp = hb.HMC_U1(L, beta, 0, 10, 0.1, n_chains=B, if_tune_step_size=False, seed=12)
+    df = torch.zeros(B, 2, L, L, dtype=torch.float64, device="cuda")
+    dp = df.clone()
+    hf.trajectories(df, 100); hp.trajectories(dp, 300, want_obs=False)
+    rf, rp = hf.trajectories(df, 40), hp.trajectories(dp, 40)
+
+    def stats(x):
+        c = x.mean(dim=0)
+        return c.mean().item(), c.std().item() / math.sqrt(B)
+    (pf, ef), (pp, ep) = stats(rf["plaq"]), stats(rp["plaq"])
+    assert abs(pf - pp) < 5 * math.hypot(ef, ep) + 1e-4, (pf, ef, pp, ep)
+    (qf, sf), (qp, sp) = stats(rf["topo"] ** 2), stats(rp["topo"] ** 2)
+    assert abs(qf - qp) < 5 * math.hypot(sf, sp) + 0.05, (qf, sf, qp, sp)

@@ -196,3 +196,51 @@ def test_step_host_pipeline_matches_resident(hb):
     r2 = h1.trajectories(d, 1)
     torch.cuda.synchronize()
     assert torch.equal(out2, d.cpu())
+
+
+def test_topological_susceptibility_matches_theory(hb):
+    """chi_t = <Q^2>/V against chi_infinity(beta) (utils.py:207-222) at a coupling where topology
+    moves freely (L=16, beta=2): 1024 chains, matched to the reference's observable definitions."""
+    from hmc_ft_b200.utils import chi_infinity, plaq_mean_theory
+    L, beta, n, dt, B = 16, 2.0, 10, 0.1, 1024
+    h = hb.HMC_U1(L, beta, 0, n, dt, n_chains=B, if_tune_step_size=False, seed=2024)
+    d = torch.zeros(B, 2, L, L, dtype=torch.float64, device="cuda")
+    h.trajectories(d, 300, want_obs=False)
+    r = h.trajectories(d, 50)
+    q2 = (r["topo"][::10] ** 2).mean(dim=0) / (L * L)          # 5 decorrelated samples per chain
+    mean, err = q2.mean().item(), q2.std().item() / math.sqrt(B)
+    assert abs(mean - chi_infinity(beta)) < 5 * err + 0.02 * chi_infinity(beta), (mean, err, chi_infinity(beta))
+    assert abs(r["topo"].mean().item()) < 0.2
+    plaq = r["plaq"].mean(dim=0)
+    assert abs(plaq.mean().item() - plaq_mean_theory(beta)) < 5 * plaq.std().item() / math.sqrt(B) + 1e-4
+
+
+def test_nan_configuration_is_rejected(hb):
+    """NaN dH compares False against the uniform draw -> reject, state unchanged (hmc_u1.py:94)."""
+    L, B = 16, 3
+    for path in (1, 2):
+        h = hb.HMC_U1(L, 2.0, 0, 5, 0.1, n_chains=B, if_tune_step_size=False, kernel_path=path)
+        d = torch.zeros(B, 2, L, L, dtype=torch.float64, device="cuda")
+        d[1, 0, 3, 3] = float("nan")
+        before = d.clone()
+        r = h.trajectories(d, 1)
+        assert r["accept"][0, 1].item() == 0 and torch.isnan(r["dH"][0, 1])
+        assert torch.equal(torch.nan_to_num(d[1], nan=7.0), torch.nan_to_num(before[1], nan=7.0))
+        assert r["accept"][0, 0].item() in (0, 1) and not torch.isnan(r["dH"][0, 0])
+
+
+def test_smallest_lattices(hb):
+    """L=2 and L=4 (every stencil wraps onto itself) through the streaming path against the oracle."""
+    for L in (2, 4):
+        g = torch.Generator().manual_seed(L)
+        B, beta, n, dt = 4, 1.3, 3, 0.2
+        th = (torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
+        pi = torch.randn(B, 2, L, L, generator=g, dtype=torch.float64)
+        u = torch.rand(B, generator=g, dtype=torch.float64)
+        o = O.PlainHMCOracle(L, beta, n, dt)
+        th_o, acc_o, H_o, dH_o = o.metropolis_step(th, pi, u)
+        h = hb.HMC_U1(L, beta, 0, n, dt, n_chains=B, if_tune_step_size=False, kernel_path=1)
+        d = th.cuda().clone()
+        r = h.trajectories(d, 1, pi.cuda().reshape(1, B, 2, L, L).contiguous(), u.cuda())
+        assert rel(r["dH"][0], dH_o) < 1e-10 and rel(d, th_o) < 1e-10
+        assert rel(h.force(th.cuda()), O.force_autograd(th, beta)) < 1e-12
