@@ -32,7 +32,7 @@ struct ConvP {
     double b[COUT];
 };
 
-enum { EPI_GELU = 0, EPI_BWD = 2 };
+enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
 
 // ---------------------------------------------------------------------------------------
 // exact-erf GELU (nn.GELU default, a = z*Phi(z)) and its derivative (Phi + z*phi) from a piecewise
@@ -81,28 +81,19 @@ static void build_gelu_table(double* out) {
     }
 }
 
-// Out-of-line GELU pair (value, derivative): the conv epilogue evaluates it 4*COUT times per thread,
-// inlining that many copies would push the kernel out of the instruction cache.
-__device__ __noinline__ double2 gelu_pair(const double* __restrict__ tab, double z) {
-    double a, d;
-    gelu_and_grad(tab, z, a, d);
-    return make_double2(a, d);
-}
-
 // out[o](x,y) = sum_{c,i,j} w[c][i*3+j][o] * in[c]((x+i-1)%L, (y+j-1)%L)   (+ epilogue)
-// One thread = a 2x2 tile of sites (x, x+1; y, y+1; both even): a 4x4 input window per channel (the
-// two centre columns as one 16-byte load) feeds 4*9*COUT DFMAs, i.e. four DFMAs per constant-bank
-// weight read; the channel loop stays rolled (weights indexed by a uniform register) so the body
-// fits the instruction cache.  Measured inner-loop rate 71 % of the DFMA peak against 64.5 % for the
-// previous two-sites-per-thread layout (tools/microbench/conv_variants.cu).
+// One thread = two vertically adjacent sites (x, x+1; x even): a 4x3 window per input channel feeds
+// 2*9*COUT DFMAs; the channel loop stays rolled (constant-bank weights indexed by a uniform register)
+// so the body fits the instruction cache.
 //   EPI_GELU : z = acc + b (+ add);  out = GELU(z);  dout = GELU'(z)            (dout may be null)
+//   EPI_FINAL: z = acc + b;  y = GELU(z);  out = atan(y)/pi/2;  dout = GELU'(z)/((1+y^2) 2pi)
 //   EPI_BWD  : out = (acc (+ add)) (* mul)
 template <int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 3)
+__global__ void __launch_bounds__(kConvThreads)
 k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
        const double* __restrict__ add, const double* __restrict__ mul,
        double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab,
-       int nquads, int L) {
+       int npairs, int L) {
     extern __shared__ double s_tab[];
     // Programmatic dependent launch: let the next kernel of the stream start its prologue while this
     // grid drains; everything before griddepcontrol.wait touches only launch-invariant data.
@@ -113,34 +104,25 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int s = blockIdx.x * kConvThreads + threadIdx.x;
-    if (s >= nquads) return;
-    const int V = L * L, H = L >> 1, QV = V >> 2;
-    const int b = s / QV, rq = s - b * QV;
-    const int xq = rq / H, yq = rq - xq * H;
-    const int x = 2 * xq, y = 2 * yq;
+    if (s >= npairs) return;
+    const int V = L * L, HV = V >> 1;
+    const int b = s / HV, rp = s - b * HV;
+    const int xp = rp / L, y = rp - xp * L, x = 2 * xp;
     const int xr[4] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x + 1) * L, (x + 2 >= L ? 0 : x + 2) * L};
-    const int ym = (y == 0 ? L - 1 : y - 1), yp = (y + 2 >= L ? 0 : y + 2);
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
     const double* ib = in + (size_t)b * CIN * V;
 
-    double acc[2][2][COUT];
+    double a0[COUT], a1[COUT];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int o = 0; o < COUT; ++o) acc[r][q][o] = 0.0;
+    for (int o = 0; o < COUT; ++o) { a0[o] = 0.0; a1[o] = 0.0; }
 #pragma unroll 1
     for (int c = 0; c < CIN; ++c) {
         const double* pc = ib + (size_t)c * V;
-        double v[4][4];
+        double v[4][3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[i][0] = pc[xr[i] + ym];
-            const double2 t = *reinterpret_cast<const double2*>(pc + xr[i] + y);
-            v[i][1] = t.x;
-            v[i][2] = t.y;
-            v[i][3] = pc[xr[i] + yp];
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[xr[i] + yc[j]];
         const double* w = p.w + c * 9 * COUT;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -149,31 +131,40 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 #pragma unroll
                 for (int o = 0; o < COUT; ++o) {
                     const double wv = w[(i * 3 + j) * COUT + o];
-#pragma unroll
-                    for (int r = 0; r < 2; ++r)
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) acc[r][q][o] = fma(wv, v[i + r][j + q], acc[r][q][o]);
+                    a0[o] = fma(wv, v[i][j], a0[o]);
+                    a1[o] = fma(wv, v[i + 1][j], a1[o]);
                 }
     }
     const size_t ob = (size_t)b * COUT * V + (size_t)x * L + y;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            const size_t idx = ob + (size_t)o * V + (size_t)r * L;          // (x+r, y), 16-byte aligned
-            if (EPI == EPI_BWD) {
-                double r0 = acc[r][0][o], r1 = acc[r][1][o];
-                if (add) { const double2 a = *reinterpret_cast<const double2*>(add + idx); r0 += a.x; r1 += a.y; }
-                if (mul) { const double2 m = *reinterpret_cast<const double2*>(mul + idx); r0 *= m.x; r1 *= m.y; }
-                *reinterpret_cast<double2*>(out + idx) = make_double2(r0, r1);
+    for (int o = 0; o < COUT; ++o) {
+        const size_t i0 = ob + (size_t)o * V, i1 = i0 + L;
+        if (EPI == EPI_BWD) {
+            double r0 = a0[o], r1 = a1[o];
+            if (add) { r0 += add[i0]; r1 += add[i1]; }
+            if (mul) { r0 *= mul[i0]; r1 *= mul[i1]; }
+            out[i0] = r0;
+            out[i1] = r1;
+        } else {
+            double z0 = a0[o] + p.b[o], z1 = a1[o] + p.b[o];
+            if (EPI == EPI_GELU && add) { z0 += add[i0]; z1 += add[i1]; }
+            double g0, d0, g1, d1;
+            gelu_and_grad(s_tab, z0, g0, d0);
+            gelu_and_grad(s_tab, z1, g1, d1);
+            if (EPI == EPI_GELU) {
+                out[i0] = g0;
+                out[i1] = g1;
+                if (dout) { dout[i0] = d0; dout[i1] = d1; }
             } else {
-                double z0 = acc[r][0][o] + p.b[o], z1 = acc[r][1][o] + p.b[o];
-                if (add) { const double2 a = *reinterpret_cast<const double2*>(add + idx); z0 += a.x; z1 += a.y; }
-                const double2 g0 = gelu_pair(s_tab, z0), g1 = gelu_pair(s_tab, z1);
-                *reinterpret_cast<double2*>(out + idx) = make_double2(g0.x, g1.x);
-                if (dout) *reinterpret_cast<double2*>(dout + idx) = make_double2(g0.y, g1.y);
+                out[i0] = atan(g0) / kPi / 2;                      // cnn_model_opt.py:46
+                out[i1] = atan(g1) / kPi / 2;
+                if (dout) {
+                    dout[i0] = d0 / ((1.0 + g0 * g0) * kTwoPi);
+                    dout[i1] = d1 / ((1.0 + g1 * g1) * kTwoPi);
+                }
             }
         }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -676,7 +667,7 @@ static long long default_chunk_sites() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_conv<kW, kW, EPI_GELU>, kConvThreads,
                                                       (size_t)kGeluTableDoubles * sizeof(double)) != cudaSuccess || nb < 1)
         return 227328;
-    return (long long)sms * nb * kConvThreads * 4 * 8;     // 8 waves (4 sites per thread): launch/ramp overheads amortised
+    return (long long)sms * nb * kConvThreads * 2 * 8;     // 8 waves: launch/ramp overheads amortised
 }
 static std::atomic<long long> g_chunk_sites{-1};
 static long long chunk_sites() {
@@ -768,10 +759,10 @@ static inline double* Dbuf(const FtWs& w, int n_layers, int C, int L, int k, int
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
-    const int nquads = nsites >> 2;
+    const int npairs = nsites >> 1;
     const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(blocks_for(nquads, kConvThreads));
+    cfg.gridDim = dim3(blocks_for(npairs, kConvThreads));
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -781,7 +772,7 @@ static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double*
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const double* tab = h->gelu_tab;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<CIN, COUT, EPI>, p, in, add, mul, out, dout, tab, nquads, L);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<CIN, COUT, EPI>, p, in, add, mul, out, dout, tab, npairs, L);
     count_launch();
     if (e != cudaSuccess) return (int)e;
     return U1_OK;
