@@ -64,7 +64,7 @@ def bench_ft(args, rank, world, dev, time_steps, arch="rnet3", L=64, beta=6.0, n
     }
 
 
-def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50, dt=0.06, halo=10, steps=3, warmup=2):
+def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50, dt=0.06, halo=None, steps=3, warmup=2):
     """BASELINE configs[4]: one L=4096 lattice, plain HMC, slab-decomposed over the ranks with a
     k-row NVLink halo exchange every k steps (hmc_ft_b200/sharding.py SlabHMC)."""
     from hmc_ft_b200.sharding import SlabHMC

@@ -96,7 +96,7 @@ class SlabHMC:
     (seed, chain, traj) only, so every rank takes the same Metropolis decision and the chain is
     identical (up to reduction round-off in dH) to the undecomposed one."""
 
-    def __init__(self, lattice_size: int, beta: float, n_steps: int, step_size: float, halo: int = 10,
+    def __init__(self, lattice_size: int, beta: float, n_steps: int, step_size: float, halo: Optional[int] = None,
                  seed: int = 1331, chain: int = 0, group=None, device=None):
         self.L, self.beta, self.n_steps, self.dt = int(lattice_size), float(beta), int(n_steps), float(step_size)
         self.group = group
@@ -105,6 +105,8 @@ class SlabHMC:
         if self.L % self.world or self.L % 2:
             raise ValueError("L must be even and divisible by the number of ranks")
         self.Lx = self.L // self.world
+        if halo is None:       # auto: trade redundant rows (2k/Lx extra compute) for fewer exchanges (one per k steps)
+            halo = max(10, self.Lx // 16)
         self.k = max(1, min(int(halo), self.Lx, self.n_steps))
         self.x0 = self.rank * self.Lx
         self.seed, self.chain = int(seed), int(chain)
