@@ -756,26 +756,10 @@ static inline double* Dbuf(const FtWs& w, int n_layers, int C, int L, int k, int
     return (double*)((char*)w.D + ((size_t)k * n_layers + layer) * f12);
 }
 
-template <int CIN, int COUT, int EPI>
-static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
-                       const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
-    const int npairs = nsites >> 1;
-    const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(blocks_for(npairs, kConvThreads));
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const double* tab = h->gelu_tab;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<CIN, COUT, EPI>, p, in, add, mul, out, dout, tab, npairs, L);
-    count_launch();
-    if (e != cudaSuccess) return (int)e;
-    return U1_OK;
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_PDL"); v = e ? atoi(e) : 1; }
+    return v != 0;
 }
 
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int blocks, size_t smem, cudaStream_t st) {
@@ -785,9 +769,24 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int b
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+}
+
+template <int CIN, int COUT, int EPI>
+static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
+                       const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
+    const int npairs = nsites >> 1;
+    const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    pdl_config(cfg, attr, blocks_for(npairs, kConvThreads), smem, st);
+    const double* tab = h->gelu_tab;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<CIN, COUT, EPI>, p, in, add, mul, out, dout, tab, npairs, L);
+    count_launch();
+    if (e != cudaSuccess) return (int)e;
+    return U1_OK;
 }
 
 static int launch_final_sparse(u1ft_handle_t h, int k, const double* in, double* Kout, double* dout,
