@@ -772,6 +772,22 @@ int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* t
     return launch_step(a, B, false, (cudaStream_t)stream);
 }
 
+int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
+                           int B, int Lx, int L, double beta, double first_drift, double dt, int n,
+                           u1_stream_t stream) {
+    g_launches = 0;
+    if (!thetaA || !piA || !thetaB || !piB || B <= 0 || L <= 0 || Lx <= 0 || n < 0) return U1_ERR_ARG;
+    if (thetaA == thetaB || piA == piB) return U1_ERR_ARG;
+    for (int s = 0; s < n; ++s) {
+        StepArgs a{};
+        a.th = (s & 1) ? thetaB : thetaA; a.pi = (s & 1) ? piB : piA;
+        a.tho = (s & 1) ? thetaA : thetaB; a.pio = (s & 1) ? piA : piB;
+        a.Lx = Lx; a.L = L; a.beta = beta; a.drift = (s == 0) ? first_drift : dt; a.kick = dt;
+        U1_TRY(launch_step(a, B, false, (cudaStream_t)stream));
+    }
+    return U1_OK;
+}
+
 int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
                     long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
     g_launches = 0;

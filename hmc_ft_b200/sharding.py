@@ -159,17 +159,18 @@ class SlabHMC:
             pi_c = cur[1, :, own].contiguous()
             dn_row = cur[0, :, k + Lx].contiguous()          # first row of the lower neighbour, [2][L]
             s_old = self._global_sums(th_c, dn_row, pi_c)
-            fresh = k                                        # valid halo depth of `cur`
-            for s in range(self.n_steps):
-                if fresh == 0:
+            done = 0
+            while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
+                if done > 0:
                     self.halo.exchange(cur)                  # theta and pi, k rows each side
-                    fresh = k
-                drift = 0.5 * dt if s == 0 else dt
-                self._call(lib.u1_leapfrog_step_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
-                                                     nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta, drift, dt, sp),
-                           "u1_leapfrog_step_rect")
-                cur, nxt = nxt, cur
-                fresh -= 1
+                nb = min(k, self.n_steps - done)
+                self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
+                                                      nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
+                                                      0.5 * dt if done == 0 else dt, dt, nb, sp),
+                           "u1_leapfrog_steps_rect")
+                if nb & 1:
+                    cur, nxt = nxt, cur
+                done += nb
             # final half drift + wrap on own rows (hmc_u1.py:78-79), then H_new
             th_new = torch.empty(2, Lx, L, dtype=torch.float64, device=dev)
             pi_c = cur[1, :, own].contiguous()

@@ -115,6 +115,12 @@ int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
 int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
                           int B, int Lx, int L, double beta, double drift, double kick,
                           u1_stream_t stream);
+/* n consecutive steps of the rectangular kernel in one call, ping-ponging between (thetaA,piA) and
+ * (thetaB,piB): step 0 reads A and writes B, step 1 reads B and writes A, ...  The first step drifts by
+ * first_drift, the others by dt; every kick is dt.  The result is in A if n is even, in B if odd. */
+int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
+                           int B, int Lx, int L, double beta, double first_drift, double dt, int n,
+                           u1_stream_t stream);
 /* Philox momenta for rows x_first .. x_first+Lx-1 (taken modulo Lx_global) of ONE global lattice of
  * Lx_global x L sites: pi[2][Lx][L].  Keyed by the global site index, so the field does not depend
  * on the decomposition. */
