@@ -29,7 +29,7 @@ def fp64_peak_tflops(lib, dev):
 
 
 def bench_ft(args, rank, world, dev, time_steps, arch="rnet3", L=64, beta=6.0, n_steps=50, dt=0.05, total=1024,
-             steps=1, warmup=1):
+             steps=2, warmup=3):
     import hmc_ft_b200 as hb
     from hmc_ft_b200 import _lib
     lib = _lib.load()
@@ -64,7 +64,7 @@ def bench_ft(args, rank, world, dev, time_steps, arch="rnet3", L=64, beta=6.0, n
     }
 
 
-def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50, dt=0.06, halo=None, steps=3, warmup=2):
+def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50, dt=0.06, halo=None, steps=3, warmup=3):
     """BASELINE configs[4]: one L=4096 lattice, plain HMC, slab-decomposed over the ranks with a
     k-row NVLink halo exchange every k steps (hmc_ft_b200/sharding.py SlabHMC)."""
     from hmc_ft_b200.sharding import SlabHMC
