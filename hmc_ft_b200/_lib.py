@@ -20,6 +20,7 @@ SIGNATURES = {
     "u1_rectangle": (_i, [_vp, _vp, _i, _i, _vp]),
     "u1_regularize": (_i, [_vp, _vp, _sz, _vp]),
     "u1_observables": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "u1_autocorr": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
     "u1_workspace_bytes": (_sz, [_i, _i]),
     "u1_action": (_i, [_vp, _vp, _i, _i, _d, _vp, _sz, _vp]),
     "u1_force": (_i, [_vp, _vp, _i, _i, _d, _vp]),
@@ -45,6 +46,9 @@ SIGNATURES = {
     "u1ft_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "u1ft_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_phase": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    "u1ft_coefficients": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    "u1ft_inverse_workspace_bytes": (_sz, [_i, _i]),
+    "u1ft_inverse_iter": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _sz, _vp]),
     "u1ft_force": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _sz, _vp]),
     "u1ft_leapfrog": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, _vp, _sz, _vp]),

@@ -399,6 +399,57 @@ k_ft_update(const double* __restrict__ th, const double* __restrict__ K, double*
     }
 }
 
+// One fixed-point iteration of the inverse transformation (field_trans_opt.py:245-282):
+// next = curr - ft_phase(iter); per-block partial sums of |next-iter|^2 and |iter|^2.
+__global__ void __launch_bounds__(kUpdThreads)
+k_ft_inverse_iter(const double* __restrict__ cur, const double* __restrict__ it, const double* __restrict__ K,
+                  double* __restrict__ nxt, double* __restrict__ partial, int k, int L, int nblk) {
+    __shared__ double red[2 * 32];
+    const int V = L * L;
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * kUpdThreads + threadIdx.x;
+    const Subset ss = subset_of(k);
+    double v[2] = {0.0, 0.0};
+    if (r < V) {
+        const int x = r / L, y = r - x * L;
+        const double* i0 = it + (size_t)b * 2 * V;
+        const double* c0 = cur + (size_t)b * 2 * V;
+        double n0 = c0[r], n1 = c0[V + r];
+        if (((x & 1) == ss.a) && ((y & 1) == ss.b)) {
+            Lat g{i0, i0 + V, L};
+            LinkTerms t;
+            link_terms(g, ss.mu, x, y, t);
+            const double* Kb = K + (size_t)b * kW * V + r;
+            double d[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                d[q] = Kb[(size_t)term_channel(ss.mu, q) * V] * (term_sign(ss.mu, q) * sin(t.A[q]));
+            const double delta = (d[0] + d[1]) + (((d[2] + d[3]) + d[4]) + d[5]);
+            if (ss.mu == 0) n0 = n0 + (-delta); else n1 = n1 + (-delta);
+        }
+        const double a0 = i0[r], a1 = i0[V + r];
+        v[0] = (n0 - a0) * (n0 - a0) + (n1 - a1) * (n1 - a1);
+        v[1] = a0 * a0 + a1 * a1;
+        double* ob = nxt + (size_t)b * 2 * V;
+        ob[r] = n0;
+        ob[V + r] = n1;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) {
+        partial[2 * ((size_t)b * nblk + blockIdx.x)] = v[0];
+        partial[2 * ((size_t)b * nblk + blockIdx.x) + 1] = v[1];
+    }
+}
+
+// norms[0..1] = sums of n partial pairs, single CTA, fixed order.
+__global__ void __launch_bounds__(256) k_sum_pairs(const double* __restrict__ partial, size_t n, double* __restrict__ norms) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0.0, 0.0};
+    for (size_t i = threadIdx.x; i < n; i += 256) { v[0] += partial[2 * i]; v[1] += partial[2 * i + 1]; }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) { norms[0] = v[0]; norms[1] = v[1]; }
+}
+
 // logdet[b] (+)= sum of partials, fixed order.
 __global__ void k_ft_logdet_accum(const double* __restrict__ partial, double* __restrict__ logdet,
                                   int B, int nblk, int first) {
@@ -1073,6 +1124,54 @@ int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
         count_launch();
         U1_CHECK_LAUNCH();
     }
+    return U1_OK;
+}
+
+int u1ft_coefficients(u1ft_handle_t h, const double* theta, int index, double* K,
+                      int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!theta || !K || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    const int Cmax = chunk_chains(B, L);
+    U1_TRY(check_ws_ft(ws, ws_bytes, carve_ft(nullptr, h->n_layers, Cmax, L, false).bytes));
+    FtWs w = carve_ft(ws, h->n_layers, Cmax, L, false);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t V = (size_t)L * L;
+    for (int b0 = 0; b0 < B; b0 += Cmax) {
+        const int C = (B - b0 < Cmax) ? B - b0 : Cmax;
+        k_ft_features<<<blocks_for((size_t)C * V, 256), 256, 0, st>>>(theta + (size_t)b0 * 2 * V, w.X, index, (int)(C * V), L);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        FtWs wk = w;
+        wk.Kk[index] = K + (size_t)b0 * kW * V;            // final layer writes straight into the caller's buffer
+        U1_TRY(cnn_forward(h, wk, index, C, L, false, st));
+    }
+    return U1_OK;
+}
+
+size_t u1ft_inverse_workspace_bytes(int B, int L) {
+    if (B <= 0 || L <= 0) return 0;
+    return al((size_t)B * blocks_for((size_t)L * L, kUpdThreads) * 2 * sizeof(double));
+}
+
+int u1ft_inverse_iter(const double* theta_curr, const double* theta_iter, const double* K, int index,
+                      double* theta_next, double* norms, int B, int L,
+                      void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_curr || !theta_iter || !K || !theta_next || !norms || B <= 0 || L <= 0 || index < 0 || index > 7)
+        return U1_ERR_ARG;
+    if (L & 1) return U1_ERR_SHAPE;
+    if (theta_next == theta_iter || theta_next == theta_curr || B > 65535) return U1_ERR_ARG;
+    U1_TRY(check_ws_ft(ws, ws_bytes, u1ft_inverse_workspace_bytes(B, L)));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = blocks_for((size_t)L * L, kUpdThreads);
+    k_ft_inverse_iter<<<dim3(nblk, B), kUpdThreads, 0, st>>>(theta_curr, theta_iter, K, theta_next, (double*)ws, index, L, nblk);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_sum_pairs<<<1, 256, 0, st>>>((const double*)ws, (size_t)B * nblk, norms);
+    count_launch();
+    U1_CHECK_LAUNCH();
     return U1_OK;
 }
 

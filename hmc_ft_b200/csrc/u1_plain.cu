@@ -564,6 +564,41 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* __restrict__ out, in
     out[blockIdx.x * 256 + threadIdx.x] = s;
 }
 
+// ---- observable post-processing (utils.py:224-298), one CTA per (lag, chain) ----
+__global__ void __launch_bounds__(256) k_series_stats(const double* __restrict__ topo, int T, int B, double* __restrict__ stats) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    double s[1] = {0.0};
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s[0] += rint(topo[(size_t)t * B + b]);
+    block_sum<1>(s, red);
+    const double mean = s[0] / T;
+    double v[1] = {0.0};
+    for (int t = threadIdx.x; t < T; t += blockDim.x) { const double d = rint(topo[(size_t)t * B + b]) - mean; v[0] += d * d; }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) { stats[2 * b] = mean; stats[2 * b + 1] = v[0] / T; }
+}
+
+__global__ void __launch_bounds__(256) k_autocorr(const double* __restrict__ topo, int T, int B, double two_v_chi,
+                                                   const double* __restrict__ stats, double* __restrict__ gchi,
+                                                   double* __restrict__ gdef) {
+    __shared__ double red[2 * 32];
+    const int d = blockIdx.x, b = blockIdx.y;
+    const double mean = stats[2 * b], var = stats[2 * b + 1];
+    double v[2] = {0.0, 0.0};
+    for (int t = threadIdx.x; t + d < T; t += blockDim.x) {
+        const double q0 = rint(topo[(size_t)t * B + b]), q1 = rint(topo[(size_t)(t + d) * B + b]);
+        v[0] += (q0 - q1) * (q0 - q1);
+        v[1] += (q0 - mean) * (q1 - mean);
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) {
+        const size_t o = (size_t)d * B + b;
+        const int n = T - d;
+        if (gchi) gchi[o] = (d == 0) ? 1.0 : 1.0 - (v[0] / n) / two_v_chi;
+        if (gdef) gdef[o] = (d == 0 || var == 0.0) ? 1.0 : (v[1] / n) / var;
+    }
+}
+
 static bool resident_supported(int L) { return L == 8 || L == 16 || L == 32 || L == 64; }
 
 template <int L, int TX, int TY>
@@ -659,6 +694,22 @@ int u1_fp64_probe(double* out, int blocks, int iters, u1_stream_t stream) {
     g_launches = 0;
     if (!out || blocks <= 0 || iters <= 0) return U1_ERR_ARG;
     k_fp64_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_autocorr(const double* topo, int T, int B, int max_lag, double two_v_chi,
+                double* gamma_chi, double* gamma_def, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!topo || T < 1 || B < 1 || max_lag < 0 || max_lag >= T || B > 65535) return U1_ERR_ARG;
+    if (gamma_chi && !(two_v_chi > 0)) return U1_ERR_ARG;
+    if (!ws || ws_bytes < (size_t)2 * B * sizeof(double) || (reinterpret_cast<uintptr_t>(ws) & 7u)) return U1_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_series_stats<<<B, 256, 0, st>>>(topo, T, B, (double*)ws);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_autocorr<<<dim3(max_lag + 1, B), 256, 0, st>>>(topo, T, B, two_v_chi, (const double*)ws, gamma_chi, gamma_def);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;

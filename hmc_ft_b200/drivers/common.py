@@ -23,7 +23,7 @@ def hmc_summary(beta, max_lag, volume, therm_plaq_ls, plaq_ls, topological_charg
     if topo.ndim == 1:
         topo = topo[:, None]
     max_lag = min(max_lag, max(1, topo.shape[0] - 1))
-    autocor = np.mean([auto_from_chi(topo[:, b], max_lag, beta, volume) for b in range(topo.shape[1])], axis=0)
+    autocor = np.asarray(auto_from_chi(topo, max_lag, beta, volume)).mean(axis=1)      # all chains in one launch
     print(f"Thermalization acceptance rate: {float(_np(therm_acceptance_rate).mean()):.4f}")
     print(f"Acceptance rate: {float(_np(acceptance_rate).mean()):.4f}")
     plaq = _np(plaq_ls)

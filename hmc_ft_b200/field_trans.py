@@ -165,6 +165,67 @@ class FieldTransformation:
         self._count()
         return self._back(out, theta, single)
 
+    def compute_K0_K1(self, theta, index, plaq=None, rect=None):
+        """field_trans_opt.py:110-135 -> (K0 [B,4,L,L], K1 [B,8,L,L]).  Only the entries ft_phase reads
+        (active sites of the subset, channels of its direction) are defined; everything else is zero.
+        plaq / rect are accepted for signature compatibility and recomputed on the device."""
+        d, single, B = self._stage(theta)
+        K = self._coefficients(d, index)
+        mask = torch.zeros_like(K, dtype=torch.bool)
+        mu, k = divmod(int(index), 4)
+        ch = [2 * mu, 2 * mu + 1] + list(range(4 + 4 * mu, 8 + 4 * mu))
+        mask[:, ch, (k >> 1) & 1::2, k & 1::2] = True
+        K = torch.where(mask, K, torch.zeros_like(K))
+        return self._back(K[:, :4], theta), self._back(K[:, 4:], theta)
+
+    def _coefficients(self, d, index):
+        B = d.shape[0]
+        K = torch.empty((B, 12, self.L, self.L), dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = self.workspace(B, False)
+            _lib.check(self._lib.u1ft_coefficients(self._handle, d.data_ptr(), int(index), K.data_ptr(), B, self.L,
+                                                   ws, nb, stream_ptr(self._dev)), "u1ft_coefficients")
+        self._count()
+        return K
+
+    def inverse(self, theta, max_iter: int = 200, tol: float = 1e-6):
+        """field_trans_opt.py:245-282: theta_ori -> theta_new by per-subset fixed-point iteration, same
+        stopping rule (global relative change < tol, tested on the host every iteration; a subset
+        that does not converge within max_iter is left unchanged, with a warning).  The subset's
+        coefficients do not depend on its own links, so the CNN runs once per subset instead of
+        once per iteration; the iterates are identical."""
+        d, single, B = self._stage(theta)
+        cur = d.clone()
+        it, nxt = torch.empty_like(cur), torch.empty_like(cur)
+        norms = torch.empty(2, dtype=torch.float64, device=self._dev)
+        self.inverse_iterations = []
+        with torch.cuda.device(self._dev):
+            ws, nb = WS.get(self._dev, self._lib.u1ft_inverse_workspace_bytes(B, self.L), "ftinv")
+            for index in reversed(range(self.n_subsets)):
+                K = self._coefficients(cur, index)
+                it.copy_(cur)
+                diff, n_it = float("inf"), 0
+                for i in range(max_iter):
+                    _lib.check(self._lib.u1ft_inverse_iter(cur.data_ptr(), it.data_ptr(), K.data_ptr(), index,
+                                                           nxt.data_ptr(), norms.data_ptr(), B, self.L, ws, nb,
+                                                           stream_ptr(self._dev)), "u1ft_inverse_iter")
+                    self._count()
+                    n = norms.tolist()                        # host sync, as `if diff < tol` in the reference
+                    diff = (n[0] ** 0.5) / (n[1] ** 0.5) if n[1] > 0 else float("nan")
+                    n_it = i + 1
+                    if diff < tol:
+                        cur.copy_(nxt)
+                        break
+                    it, nxt = nxt, it
+                if not diff < tol:
+                    self.print(f"Warning: Inverse iteration for subset {index} did not converge, final diff = {diff:.2e}")
+                self.inverse_iterations.append(n_it)
+        return self._back(cur, theta, single)
+
+    def inverse_field_transformation(self, theta):
+        """field_trans_opt.py:280-282."""
+        return self.inverse(theta)
+
     # torch.compile aliases of the reference (field_trans_opt.py:83-108)
     forward_compiled = forward
     field_transformation_compiled = field_transformation

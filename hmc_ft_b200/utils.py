@@ -138,23 +138,36 @@ def chi_infinity(beta: float) -> float:
     return num / den
 
 
-def auto_from_chi(topo, max_lag: int, beta: float, volume: int) -> np.ndarray:
-    """utils.py:224-262: Gamma(d) = 1 - <(Q_t - Q_{t+d})^2> / (2 V chi_inf)."""
-    topo = np.round(np.asarray(topo)).astype(int)
-    chi = chi_infinity(beta)
-    out = np.ones(max_lag + 1)
-    for d in range(1, max_lag + 1):
-        out[d] = 1 - np.mean((topo[:-d] - topo[d:]) ** 2) / (2 * volume * chi)
-    return out
+def _autocorr(topo, max_lag: int, two_v_chi: float, which: str):
+    """Device evaluation for one history [T] or a batch [T,B]; returns the input's kind (numpy in ->
+    numpy out, tensor in -> tensor on the same device)."""
+    lib = _lib.load()
+    as_np = not torch.is_tensor(topo)
+    t = torch.as_tensor(np.asarray(topo, dtype=np.float64)) if as_np else topo
+    single = t.dim() == 1
+    t2 = t.reshape(t.shape[0], -1)
+    dev = require_cuda(t2.device if t2.is_cuda else None)
+    d = to_dev(t2, dev)
+    T, B = d.shape
+    if max_lag >= T:
+        raise ValueError("max_lag must be smaller than the history length")
+    out = torch.empty((max_lag + 1, B), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws, nb = WS.get(dev, 16 * B + 256, "autocorr")
+        args = (out.data_ptr(), None) if which == "chi" else (None, out.data_ptr())
+        _lib.check(lib.u1_autocorr(d.data_ptr(), T, B, int(max_lag), float(two_v_chi), args[0], args[1], ws, nb,
+                                   stream_ptr(dev)), "u1_autocorr")
+    out = out[:, 0] if single else out
+    if as_np:
+        return out.cpu().numpy()
+    return out if t.is_cuda else out.to(t.device)
 
 
-def auto_by_def(topo, max_lag: int) -> np.ndarray:
-    """utils.py:264-298."""
-    topo = np.round(np.asarray(topo)).astype(int)
-    mean, var = np.mean(topo), np.var(topo)
-    if var == 0:
-        return np.ones(max_lag + 1)
-    out = np.ones(max_lag + 1)
-    for d in range(1, max_lag + 1):
-        out[d] = np.mean((topo[:-d] - mean) * (topo[d:] - mean)) / var
-    return out
+def auto_from_chi(topo, max_lag: int, beta: float, volume: int):
+    """utils.py:224-262: Gamma(d) = 1 - <(Q_t - Q_{t+d})^2> / (2 V chi_inf); [T] or [T,B] histories."""
+    return _autocorr(topo, max_lag, 2 * volume * chi_infinity(beta), "chi")
+
+
+def auto_by_def(topo, max_lag: int):
+    """utils.py:264-298: normalised autocovariance; [T] or [T,B] histories."""
+    return _autocorr(topo, max_lag, 1.0, "def")

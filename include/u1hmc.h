@@ -50,6 +50,14 @@ int u1_regularize(const double* in, double* out, size_t n, u1_stream_t stream);
 int u1_observables(const double* theta, double* plaq_mean, double* topo, int B, int L,
                    void* ws, size_t ws_bytes, u1_stream_t stream);
 
+/* utils.py:224-298  auto_from_chi / auto_by_def for B chains at once.  topo: [T][B] topological-charge
+ * histories (rounded to the nearest integer like the reference).  gamma_chi[d][b] =
+ * 1 - <(Q_t-Q_{t+d})^2> / two_v_chi with two_v_chi = 2*V*chi_inf(beta) (utils.py:207-222, a host
+ * constant); gamma_def[d][b] = autocovariance / variance (all ones if the variance is zero).
+ * Outputs are [max_lag+1][B]; either may be NULL.  ws: 2*B doubles. */
+int u1_autocorr(const double* topo, int T, int B, int max_lag, double two_v_chi,
+                double* gamma_chi, double* gamma_def, void* ws, size_t ws_bytes, u1_stream_t stream);
+
 /* ---------------- HMC_U1 (hmc_u1.py) ---------------- */
 size_t u1_workspace_bytes(int B, int L);
 /* hmc_u1.py:56-63  action(theta) -> S[b]. */
@@ -169,6 +177,22 @@ int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double
 /* field_trans_opt.py:137-217  ft_phase(theta, index) -> Delta[b][2][x][y] (diagnostic surface). */
 int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
                int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* field_trans_opt.py:110-135  compute_K0_K1 of subset `index`: K[b][12][x][y] (channels 0..3 = K0,
+ * 4..11 = K1).  Only the entries the transformation reads are defined: the active sites of the subset
+ * and the 6 channels of its direction (the rest is multiplied by the field mask in ft_phase and is
+ * left untouched here). */
+int u1ft_coefficients(u1ft_handle_t h, const double* theta, int index, double* K,
+                      int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* One fixed-point iteration of field_trans_opt.py:245-282 (inverse) for subset `index` with the
+ * coefficients K of u1ft_coefficients (they do not depend on the subset's own links, so one CNN
+ * evaluation serves every iteration):  theta_next = theta_curr - ft_phase(theta_iter, index), and
+ * norms[0] = |theta_next - theta_iter|^2, norms[1] = |theta_iter|^2 summed over the whole batch
+ * (device doubles; the caller takes the square roots and tests the tolerance, as the reference
+ * does on the host).  ws: u1ft_inverse_workspace_bytes(B, L). */
+size_t u1ft_inverse_workspace_bytes(int B, int L);
+int u1ft_inverse_iter(const double* theta_curr, const double* theta_iter, const double* K, int index,
+                      double* theta_next, double* norms, int B, int L,
+                      void* ws, size_t ws_bytes, u1_stream_t stream);
 /* hmc_u1_ft.py:101-125  new_action = S(F(theta)) - logdet.  Optional extra outputs. */
 int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* theta_ori,
                 double* logdet, int B, int L, double beta,

@@ -284,6 +284,25 @@ class FieldTransformationOracle:
             cur = cur + self.ft_phase(cur, k)
         return cur
 
+    def inverse(self, theta, max_iter: int = 200, tol: float = 1e-6):
+        """field_trans_opt.py:245-282: per-subset fixed-point iteration in reverse subset order;
+        returns (theta_new, iterations per subset in the order visited)."""
+        cur = theta.clone()
+        iters = []
+        for index in reversed(range(8)):
+            it = cur.clone()
+            diff, n_it = float("inf"), 0
+            for i in range(max_iter):
+                nxt = cur + (-self.ft_phase(it, index))
+                diff = torch.norm(nxt - it) / torch.norm(it)
+                n_it = i + 1
+                if diff < tol:
+                    cur = nxt
+                    break
+                it = nxt
+            iters.append(n_it)
+        return cur, iters
+
     def forward_and_logdet(self, theta):
         """field_trans_opt.py:284-383 (one CNN evaluation per subset instead of two;
         identical values)."""
@@ -452,3 +471,36 @@ def philox_accept_uniform(seed: int, chain: int, traj: int) -> float:
                      ((seed >> 32) & 0xFFFFFFFF) ^ (chain & 0xFFFFFFFF)]], dtype=np.uint32)
     r = philox4x32_10(ctr, key)
     return float(u01_from_bits(r[:, 0], r[:, 1])[0])
+
+
+# --------------------------------------------------------------------------
+# Observable post-processing (utils.py:207-298) — numpy, as in the reference
+# --------------------------------------------------------------------------
+def chi_infinity(beta: float) -> float:
+    """utils.py:207-222."""
+    from scipy.integrate import quad
+    num, _ = quad(lambda p: (p / (2 * math.pi)) ** 2 * math.exp(beta * math.cos(p)), -math.pi, math.pi)
+    den, _ = quad(lambda p: math.exp(beta * math.cos(p)), -math.pi, math.pi)
+    return num / den
+
+
+def auto_from_chi(topo, max_lag: int, beta: float, volume: int) -> np.ndarray:
+    """utils.py:224-262: Gamma(d) = 1 - <(Q_t - Q_{t+d})^2> / (2 V chi_inf), Gamma(0) = 1."""
+    topo = np.round(np.asarray(topo)).astype(int)
+    chi = chi_infinity(beta)
+    out = np.zeros(max_lag + 1)
+    for d in range(max_lag + 1):
+        out[d] = 1.0 if d == 0 else 1 - np.mean((topo[:-d] - topo[d:]) ** 2) / (2 * volume * chi)
+    return out
+
+
+def auto_by_def(topo, max_lag: int) -> np.ndarray:
+    """utils.py:264-298: normalised autocovariance, all ones if the variance vanishes."""
+    topo = np.round(np.asarray(topo)).astype(int)
+    mean, var = np.mean(topo), np.var(topo)
+    if var == 0:
+        return np.ones(max_lag + 1)
+    out = np.zeros(max_lag + 1)
+    for d in range(max_lag + 1):
+        out[d] = 1.0 if d == 0 else np.mean((topo[:-d] - mean) * (topo[d:] - mean)) / var
+    return out

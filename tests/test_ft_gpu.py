@@ -259,3 +259,23 @@ def test_fthmc_matches_plain_hmc_ensemble(golden_dir):
     assert abs(pf - pp) < 5 * math.hypot(ef, ep) + 1e-4, (pf, ef, pp, ep)
     (qf, sf), (qp, sp) = stats(rf["topo"] ** 2), stats(rp["topo"] ** 2)
     assert abs(qf - qp) < 5 * math.hypot(sf, sp) + 0.05, (qf, sf, qp, sp)
+
+
+@pytest.mark.parametrize("tag,wfile", [("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L16", "weights_simple_beta6.0.npz")])
+def test_inverse_and_coefficients(golden_dir, tag, wfile):
+    """FieldTransformation.inverse (field_trans_opt.py:245-282) and compute_K0_K1 (:110-135) against the
+    reference's outputs; iteration counts against the oracle (same global stopping rule)."""
+    z = np.load(os.path.join(golden_dir, f"inverse_{tag}.npz"))
+    L = int(z["L"])
+    ft = make_ft(golden_dir, L, wfile)
+    back = ft.inverse(torch.tensor(z["theta_ori"], device="cuda"))
+    assert rel(back, z["inverse"]) < 1e-12
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    _, iters = O.FieldTransformationOracle(L, nets).inverse(torch.tensor(z["theta_ori"]))
+    assert ft.inverse_iterations == iters
+    assert rel(ft.inverse_field_transformation(torch.tensor(z["theta_ori"][0])), z["inverse"][0]) < 1e-6   # single config, own stopping point
+    K0, K1 = ft.compute_K0_K1(torch.tensor(z["theta_new"], device="cuda"), 6)
+    m = np.zeros_like(z["K1_6"], dtype=bool); m[:, 4:8, 1::2, 0::2] = True      # subset 6: mu=1, parity (1,0)
+    assert rel(K1.cpu().numpy()[m], z["K1_6"][m]) < 1e-12
+    m0 = np.zeros_like(z["K0_6"], dtype=bool); m0[:, 2:4, 1::2, 0::2] = True
+    assert rel(K0.cpu().numpy()[m0], z["K0_6"][m0]) < 1e-12 and float(K0[:, :2].abs().max()) == 0.0

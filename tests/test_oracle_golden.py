@@ -130,3 +130,24 @@ def test_philox_known_answers():
     p = O.philox_momenta(1331, 5, 17, 16)
     assert p.shape == (2, 16, 16) and abs(p.mean()) < 0.2 and 0.8 < p.std() < 1.2
     assert 0.0 < O.philox_accept_uniform(1331, 5, 17) < 1.0
+
+
+def test_autocorrelation_matches_reference(golden_dir):
+    """utils.py:207-298 (chi_infinity, auto_from_chi, auto_by_def) against reference outputs."""
+    z = np.load(os.path.join(golden_dir, "autocorr.npz"))
+    assert abs(O.chi_infinity(3.0) - float(z["chi_inf"])) < 1e-15 and abs(O.chi_infinity(6.0) - float(z["chi_inf_b6"])) < 1e-15
+    for b in range(z["topo"].shape[1]):
+        a = O.auto_from_chi(z["topo"][:, b], int(z["max_lag"]), float(z["beta"]), int(z["volume"]))
+        d = O.auto_by_def(z["topo"][:, b], int(z["max_lag"]))
+        assert np.array_equal(a, z["auto_from_chi"][:, b]) and np.array_equal(d, z["auto_by_def"][:, b])
+
+
+@pytest.mark.parametrize("tag,wfile", [("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L16", "weights_simple_beta6.0.npz")])
+def test_inverse_matches_reference(golden_dir, tag, wfile):
+    """field_trans_opt.py:245-282 inverse (same stopping rule) against the reference's output."""
+    z = np.load(os.path.join(golden_dir, f"inverse_{tag}.npz"))
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    ft = O.FieldTransformationOracle(int(z["L"]), nets)
+    back, iters = ft.inverse(T(z["theta_ori"]))
+    assert rel(back, z["inverse"]) < 1e-13 and max(iters) < 200
+    assert rel(back, z["theta_new"]) < 1e-4                      # debug/check_ft.py:113-118 threshold

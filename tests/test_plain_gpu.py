@@ -244,3 +244,17 @@ def test_smallest_lattices(hb):
         r = h.trajectories(d, 1, pi.cuda().reshape(1, B, 2, L, L).contiguous(), u.cuda())
         assert rel(r["dH"][0], dH_o) < 1e-10 and rel(d, th_o) < 1e-10
         assert rel(h.force(th.cuda()), O.force_autograd(th, beta)) < 1e-12
+
+
+def test_autocorrelation_device(hb, golden_dir):
+    """u1_autocorr against the reference's auto_from_chi / auto_by_def outputs (batched over chains)."""
+    from hmc_ft_b200 import utils as U
+    z = np.load(os.path.join(golden_dir, "autocorr.npz"))
+    topo, ml, beta, vol = z["topo"], int(z["max_lag"]), float(z["beta"]), int(z["volume"])
+    assert abs(U.chi_infinity(beta) - float(z["chi_inf"])) < 1e-15
+    g = U.auto_from_chi(torch.tensor(topo, device="cuda"), ml, beta, vol)
+    assert g.shape == (ml + 1, topo.shape[1]) and rel(g, z["auto_from_chi"]) < 1e-14
+    d = U.auto_by_def(torch.tensor(topo, device="cuda"), ml)
+    assert rel(d, z["auto_by_def"]) < 1e-12 and torch.all(d[:, 3] == 1.0)        # frozen chain -> all ones
+    one = U.auto_from_chi(topo[:, 0], ml, beta, vol)                              # numpy in -> numpy out
+    assert isinstance(one, np.ndarray) and one.shape == (ml + 1,) and rel(one, z["auto_from_chi"][:, 0]) < 1e-14
