@@ -183,54 +183,57 @@ k_conv_tile(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ 
     }
 }
 
-// input tile staged in shared memory with cp.async (3-stage ring over channels); block = 128 threads =
-// (128/L) row-pairs of full rows (L in {16,32,64,128}); weights from the constant bank as before.
-template <int LL, int THREADS, int MINB>
+// input tile staged in shared memory with cp.async (STAGES-deep ring over channels); block = THREADS
+// threads = (THREADS/L) groups of ROWS full rows (L in {16,32,64,128}); weights from the constant bank.
+template <int LL, int ROWS, int STAGES, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_conv_cpasync(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, int ngroups, int L) {
-    constexpr int CIN = 12, COUT = 12, STAGES = 3;
-    constexpr int TP = THREADS / LL;                  // row pairs per block
-    constexpr int TROWS = 2 * TP + 2;                 // tile rows incl. halo
+    constexpr int CIN = 12, COUT = 12;
+    constexpr int TP = THREADS / LL;                  // row groups per block
+    constexpr int TROWS = ROWS * TP + 2;              // tile rows incl. halo
     constexpr int TILE = TROWS * LL;                  // doubles per channel tile
     __shared__ __align__(16) double tile[STAGES][TILE];
     const int V = LL * LL;
-    const int pairs_per_chain = V / 2;
-    const int s0 = blockIdx.x * THREADS;              // first pair of this block (blocks never straddle chains: THREADS | V/2)
-    const int b = s0 / pairs_per_chain, rp0 = s0 - b * pairs_per_chain;
-    const int xp0 = rp0 / LL;                         // first row pair
+    const int groups_per_chain = V / ROWS;
+    const int s0 = blockIdx.x * THREADS;
+    const int b = s0 / groups_per_chain, rp0 = s0 - b * groups_per_chain;
+    const int xg0 = rp0 / LL;                         // first row group
     const int tid = threadIdx.x;
-    const int tp = tid / LL, y = tid - tp * LL;       // my row pair within the block, my column
-    const int x = 2 * (xp0 + tp);
+    const int tp = tid / LL, y = tid - tp * LL;
+    const int x = ROWS * (xg0 + tp);
     const double* ib = in + (size_t)b * CIN * V;
     auto issue = [&](int c, int stage) {
         const double* pc = ib + (size_t)c * V;
-        // tile row r corresponds to lattice row (2*xp0 - 1 + r) mod L ; copy 16-byte chunks
         constexpr int CHUNKS = TILE / 2;
         for (int q = tid; q < CHUNKS; q += THREADS) {
             const int r = (2 * q) / LL, col = 2 * q - r * LL;
-            int xx = 2 * xp0 - 1 + r; xx = xx < 0 ? xx + LL : (xx >= LL ? xx - LL : xx);
+            int xx = ROWS * xg0 - 1 + r; xx = xx < 0 ? xx + LL : (xx >= LL ? xx - LL : xx);
             const double* src = pc + xx * LL + col;
             const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[stage][r * LL + col]);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src));
         }
         asm volatile("cp.async.commit_group;");
     };
-    double a0[COUT], a1[COUT];
+    double acc[ROWS][COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) { a0[o] = 0.0; a1[o] = 0.0; }
-    issue(0, 0);
-    issue(1, 1);
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st) issue(st, st);
     const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
-    const int r0 = 2 * tp;                            // tile row of lattice row x-1
+    const int r0 = ROWS * tp;
 #pragma unroll 1
     for (int c = 0; c < CIN; ++c) {
-        if (c + 1 < CIN) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+        // groups committed so far: min(CIN, c + STAGES - 1); need group c complete
+        if (c + STAGES - 1 <= CIN) asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 2));
+        else asm volatile("cp.async.wait_group 0;");
         __syncthreads();
-        if (c + 2 < CIN) issue(c + 2, (c + 2) % STAGES);
+        if (c + STAGES - 1 < CIN) issue(c + STAGES - 1, (c + STAGES - 1) % STAGES);
         const double* t = tile[c % STAGES];
-        double v[4][3];
+        double v[ROWS + 2][3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[i][0] = t[(r0 + i) * LL + ym]; v[i][1] = t[(r0 + i) * LL + y]; v[i][2] = t[(r0 + i) * LL + yp]; }
+        for (int i = 0; i < ROWS + 2; ++i) { v[i][0] = t[(r0 + i) * LL + ym]; v[i][1] = t[(r0 + i) * LL + y]; v[i][2] = t[(r0 + i) * LL + yp]; }
         const double* w = p.w + c * 9 * COUT;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -239,15 +242,14 @@ k_conv_cpasync(const __grid_constant__ ConvP<12, 12> p, const double* __restrict
 #pragma unroll
                 for (int o = 0; o < COUT; ++o) {
                     const double wv = w[(i * 3 + j) * COUT + o];
-                    a0[o] = fma(wv, v[i][j], a0[o]);
-                    a1[o] = fma(wv, v[i + 1][j], a1[o]);
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
                 }
     }
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) {
-        out[(size_t)b * COUT * V + (size_t)o * V + (size_t)x * LL + y] = a0[o];
-        out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + 1) * LL + y] = a1[o];
-    }
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * LL + y] = acc[r][o];
 }
 
 // software-pipelined: the window of channel c+1 is loaded while channel c is being accumulated
@@ -403,10 +405,11 @@ int main(int argc, char** argv) {
         report("TILE " #TR "x" #TC " halves" #NH " t" #T " minb" #MB, ms); }
     if (argc > 2 && atoi(argv[2]) == 5) {
         RUN(2, 2, 128, 1)
-#define RUNC(T, MB) { int ng = B * V / 2; float ms = time_it([&] { k_conv_cpasync<64, T, MB><<<ng / T, T>>>(p, in, out2, ng, L); }); \
-        report("CPASYNC rows2 t" #T " minb" #MB, ms); }
-        RUNC(128, 1) RUNC(128, 4) RUNC(128, 6) RUNC(256, 1) RUNC(256, 3) RUNC(64, 8)
-        { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); k_conv_cpasync<64, 128, 1><<<ng / 128, 128>>>(p, in, out2, ng, L); }
+#define RUNC(ROWS, ST, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_cpasync<64, ROWS, ST, T, MB><<<ng / T, T>>>(p, in, out2, ng, L); }); \
+        report("CPASYNC rows" #ROWS " stages" #ST " t" #T " minb" #MB, ms); }
+        RUNC(2, 3, 128, 6) RUNC(2, 3, 128, 5) RUNC(2, 3, 128, 7) RUNC(2, 4, 128, 6) RUNC(2, 2, 128, 6) RUNC(2, 3, 256, 3) RUNC(2, 3, 64, 12)
+        RUNC(4, 3, 128, 3) RUNC(4, 3, 128, 4) RUNC(4, 3, 64, 6) RUNC(4, 3, 64, 8) RUNC(4, 4, 128, 3) RUNC(1, 3, 128, 8) RUNC(1, 3, 128, 12)
+        { int ng = B * V / 2; k_conv<2, 2, 128, 1><<<(ng + 127) / 128, 128>>>(p, in, out, ng, L); k_conv_cpasync<64, 4, 3, 128, 3><<<(ng / 2) / 128, 128>>>(p, in, out2, ng / 2, L); }
         std::vector<double> a(n), b2(n);
         cudaMemcpy(a.data(), out, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b2.data(), out2, n * 8, cudaMemcpyDeviceToHost);
         double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs(a[i] - b2[i]));
