@@ -168,6 +168,112 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------------------
+// Shared-memory tiled variant for L in {32, 64, 128}: a CTA of 128 threads owns 128/L groups of ROWS
+// complete lattice rows; per input channel the (ROWS*128/L + 2) x L tile (one halo row above and
+// below, columns wrap inside the row) is staged by cp.async into a 3-deep ring, so the next two
+// channels stream in while the current one feeds the DFMAs and the window reads become LDS.
+// Inner loop measured at 72.9 % (ROWS=2) / 76.6 % (ROWS=4) of the DFMA peak against 64 % for the
+// direct-load kernel (tools/microbench/conv_variants.cu, profiles/conv_variants5.log).  Forward
+// layers use ROWS=2 (24 inlined GELU evaluations keep the code in the instruction cache), reverse
+// layers ROWS=4.  Same epilogues and launch protocol as k_conv.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileStages = 3;
+
+template <int LL, int ROWS, int CIN, int COUT, int EPI>
+__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? 4 : 5))
+k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
+            const double* __restrict__ add, const double* __restrict__ mul,
+            double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
+    constexpr int TP = kConvThreads / LL;             // row groups per CTA
+    constexpr int TROWS = ROWS * TP + 2;              // tile rows incl. halo
+    constexpr int TILE = TROWS * LL;                  // doubles per channel tile
+    constexpr int V = LL * LL;
+    extern __shared__ __align__(16) double s_dyn[];
+    double* tile = s_dyn;                             // [kTileStages][TILE]
+    double* s_tab = s_dyn + kTileStages * TILE;       // GELU table (forward epilogues only)
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (EPI != EPI_BWD) {
+        for (int i = threadIdx.x; i < kGeluTableDoubles; i += kConvThreads) s_tab[i] = gelu_tab[i];
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    constexpr int groups_per_chain = V / ROWS;
+    const int s0 = blockIdx.x * kConvThreads;
+    const int b = s0 / groups_per_chain, rp0 = s0 - b * groups_per_chain;
+    const int xg0 = rp0 / LL;
+    const int tid = threadIdx.x;
+    const int tp = tid / LL, y = tid - tp * LL;
+    const int x = ROWS * (xg0 + tp);
+    const double* ib = in + (size_t)b * CIN * V;
+    auto issue = [&](int c, int stage) {
+        const double* pc = ib + (size_t)c * V;
+        constexpr int CHUNKS = TILE / 2;
+        for (int q = tid; q < CHUNKS; q += kConvThreads) {
+            const int r = (2 * q) / LL, col = 2 * q - r * LL;
+            int xx = ROWS * xg0 - 1 + r;
+            xx = xx < 0 ? xx + LL : (xx >= LL ? xx - LL : xx);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + stage * TILE + r * LL + col);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pc + xx * LL + col));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+#pragma unroll
+    for (int st = 0; st < kTileStages - 1; ++st) issue(st, st);
+    const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
+    const int r0 = ROWS * tp;
+#pragma unroll 1
+    for (int c = 0; c < CIN; ++c) {
+        if (c + kTileStages - 1 <= CIN) asm volatile("cp.async.wait_group %0;" ::"n"(kTileStages - 2));
+        else asm volatile("cp.async.wait_group 0;");
+        __syncthreads();                              // tile c visible; buffer of tile c-1 free (also covers s_tab)
+        if (c + kTileStages - 1 < CIN) issue(c + kTileStages - 1, (c + kTileStages - 1) % kTileStages);
+        const double* t = tile + (c % kTileStages) * TILE;
+        double v[ROWS + 2][3];
+#pragma unroll
+        for (int i = 0; i < ROWS + 2; ++i) {
+            v[i][0] = t[(r0 + i) * LL + ym];
+            v[i][1] = t[(r0 + i) * LL + y];
+            v[i][2] = t[(r0 + i) * LL + yp];
+        }
+        const double* w = p.w + c * 9 * COUT;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    const double wv = w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
+                }
+    }
+    const size_t ob = (size_t)b * COUT * V + (size_t)x * LL + y;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const size_t idx = ob + (size_t)o * V + (size_t)r * LL;
+            if (EPI == EPI_BWD) {
+                double rv = acc[r][o];
+                if (add) rv += add[idx];
+                if (mul) rv *= mul[idx];
+                out[idx] = rv;
+            } else {
+                double z = acc[r][o] + p.b[o];
+                if (add) z += add[idx];
+                double g, d;
+                gelu_and_grad(s_tab, z, g, d);
+                out[idx] = g;
+                if (dout) dout[idx] = d;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------
 // Lattice angle helpers (utils.py:118-141) with periodic wrap; x,y may be off by up to 2.
 // ---------------------------------------------------------------------------------------
 struct Lat {
@@ -825,9 +931,35 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int b
     cfg.numAttrs = 1;
 }
 
+template <int LL, int CIN, int COUT, int EPI>
+static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
+                            const double* mul, double* out, double* dout, int nsites, cudaStream_t st) {
+    constexpr int ROWS = (EPI == EPI_BWD) ? 4 : 2;
+    constexpr int TILE = (ROWS * (kConvThreads / LL) + 2) * LL;
+    constexpr size_t smem = ((size_t)kTileStages * TILE + (EPI == EPI_BWD ? 0 : kGeluTableDoubles)) * sizeof(double);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    pdl_config(cfg, attr, nsites / (ROWS * kConvThreads), smem, st);
+    const double* tab = h->gelu_tab;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tile<LL, ROWS, CIN, COUT, EPI>, p, in, add, mul, out, dout, tab);
+    count_launch();
+    return e == cudaSuccess ? U1_OK : (int)e;
+}
+
+static bool tile_path_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_TILE"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
+    if (tile_path_enabled()) {
+        if (L == 64) return launch_conv_tile<64, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+        if (L == 32) return launch_conv_tile<32, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+        if (L == 128) return launch_conv_tile<128, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+    }
     const int npairs = nsites >> 1;
     const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
     cudaLaunchConfig_t cfg;
