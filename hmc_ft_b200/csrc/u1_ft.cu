@@ -937,6 +937,12 @@ static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const do
     constexpr int ROWS = (EPI == EPI_BWD) ? 4 : 2;
     constexpr int TILE = (ROWS * (kConvThreads / LL) + 2) * LL;
     constexpr size_t smem = ((size_t)kTileStages * TILE + (EPI == EPI_BWD ? 0 : kGeluTableDoubles)) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        const char* cv = getenv("U1FT_CARVEOUT");
+        if (cv) cudaFuncSetAttribute(k_conv_tile<LL, ROWS, CIN, COUT, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+        configured = true;
+    }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     pdl_config(cfg, attr, nsites / (ROWS * kConvThreads), smem, st);
