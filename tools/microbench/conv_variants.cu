@@ -252,6 +252,133 @@ k_conv_cpasync(const __grid_constant__ ConvP<12, 12> p, const double* __restrict
         for (int o = 0; o < COUT; ++o) out[(size_t)b * COUT * V + (size_t)o * V + (size_t)(x + r) * LL + y] = acc[r][o];
 }
 
+// ---- forward-layer variants: same inner loops plus the table-GELU epilogue of the library ----
+constexpr int kGI = 136, kGD = 11, kGS = 13;
+__device__ __forceinline__ void gelu_tab_eval(const double* __restrict__ tab, double z, double& a, double& d) {
+    const double zc = fmin(fmax(z, -8.5), 8.5 - 1e-9);
+    const int i = __double2int_rd((zc + 8.5) * 8.0);
+    const double t = zc - (((double)i + 0.5) * 0.125 - 8.5);
+    const double* q = tab + i * kGS;
+    double p = q[kGD], dp = 0.0;
+#pragma unroll
+    for (int k = kGD - 1; k >= 0; --k) { dp = fma(dp, t, p); p = fma(p, t, q[k]); }
+    a = z * p; d = fma(z, dp, p);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_fwd_direct(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, double* __restrict__ dout,
+             const double* __restrict__ gtab, int npairs, int L) {
+    constexpr int CIN = 12, COUT = 12;
+    extern __shared__ double s_tab[];
+    for (int i = threadIdx.x; i < kGI * kGS; i += 128) s_tab[i] = gtab[i];
+    __syncthreads();
+    const int s = blockIdx.x * 128 + threadIdx.x;
+    if (s >= npairs) return;
+    const int V = L * L, HV = V >> 1;
+    const int b = s / HV, rp = s - b * HV;
+    const int xp = rp / L, y = rp - xp * L, x = 2 * xp;
+    const int xr[4] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x + 1) * L, (x + 2 >= L ? 0 : x + 2) * L};
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * CIN * V;
+    double a0[COUT], a1[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) { a0[o] = 0.0; a1[o] = 0.0; }
+#pragma unroll 1
+    for (int c = 0; c < CIN; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = pc[xr[i] + yc[j]];
+        const double* w = p.w + c * 9 * COUT;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) { const double wv = w[(i * 3 + j) * COUT + o]; a0[o] = fma(wv, v[i][j], a0[o]); a1[o] = fma(wv, v[i + 1][j], a1[o]); }
+    }
+    const size_t ob = (size_t)b * COUT * V + (size_t)x * L + y;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        const size_t i0 = ob + (size_t)o * V, i1 = i0 + L;
+        double g0, d0, g1, d1;
+        gelu_tab_eval(s_tab, a0[o] + p.b[o], g0, d0);
+        gelu_tab_eval(s_tab, a1[o] + p.b[o], g1, d1);
+        out[i0] = g0; out[i1] = g1; dout[i0] = d0; dout[i1] = d1;
+    }
+}
+
+template <int LL, int ROWS, int NH, int MINB>      // cp.async tile, ROWS rows per thread, output channels in NH passes
+__global__ void __launch_bounds__(128, MINB)
+k_fwd_tile(const __grid_constant__ ConvP<12, 12> p, const double* __restrict__ in, double* __restrict__ out, double* __restrict__ dout,
+           const double* __restrict__ gtab) {
+    constexpr int CIN = 12, COUT = 12, CH = COUT / NH, STAGES = 3, THREADS = 128;
+    constexpr int TP = THREADS / LL, TROWS = ROWS * TP + 2, TILE = TROWS * LL, V = LL * LL;
+    extern __shared__ __align__(16) double s_dyn[];
+    double* tile = s_dyn;
+    double* s_tab = s_dyn + STAGES * TILE;
+    for (int i = threadIdx.x; i < kGI * kGS; i += THREADS) s_tab[i] = gtab[i];
+    constexpr int groups_per_chain = V / ROWS;
+    const int s0 = blockIdx.x * THREADS;
+    const int b = s0 / groups_per_chain, rp0 = s0 - b * groups_per_chain;
+    const int xg0 = rp0 / LL, tid = threadIdx.x, tp = tid / LL, y = tid - tp * LL, x = ROWS * (xg0 + tp);
+    const double* ib = in + (size_t)b * CIN * V;
+    auto issue = [&](int c, int stage) {
+        const double* pc = ib + (size_t)c * V;
+        for (int q = tid; q < TILE / 2; q += THREADS) {
+            const int r = (2 * q) / LL, col = 2 * q - r * LL;
+            int xx = ROWS * xg0 - 1 + r; xx = xx < 0 ? xx + LL : (xx >= LL ? xx - LL : xx);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + stage * TILE + r * LL + col);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(pc + xx * LL + col));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1), r0 = ROWS * tp;
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+        double acc[ROWS][CH];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int o = 0; o < CH; ++o) acc[r][o] = 0.0;
+        __syncthreads();                                  // ring buffers free again (second pass)
+        issue(0, 0); issue(1, 1);
+#pragma unroll 1
+        for (int c = 0; c < CIN; ++c) {
+            if (c + 2 <= CIN) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            if (c + 2 < CIN) issue(c + 2, (c + 2) % STAGES);
+            const double* t = tile + (c % STAGES) * TILE;
+            double v[ROWS + 2][3];
+#pragma unroll
+            for (int i = 0; i < ROWS + 2; ++i) { v[i][0] = t[(r0 + i) * LL + ym]; v[i][1] = t[(r0 + i) * LL + y]; v[i][2] = t[(r0 + i) * LL + yp]; }
+            const double* w = p.w + c * 9 * COUT + h * CH;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int o = 0; o < CH; ++o) {
+                        const double wv = w[(i * 3 + j) * COUT + o];
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
+                    }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int o = 0; o < CH; ++o) {
+                const size_t idx = (size_t)b * COUT * V + (size_t)(h * CH + o) * V + (size_t)(x + r) * LL + y;
+                double g, d;
+                gelu_tab_eval(s_tab, acc[r][o] + p.b[h * CH + o], g, d);
+                out[idx] = g; dout[idx] = d;
+            }
+    }
+}
+
 // software-pipelined: the window of channel c+1 is loaded while channel c is being accumulated
 template <int ROWS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -403,6 +530,25 @@ int main(int argc, char** argv) {
     }
 #define RUNT(TR, TC, NH, T, MB) { int ng = B * V / (TR * TC); float ms = time_it([&] { k_conv_tile<TR, TC, NH, T, MB><<<(ng + T - 1) / T, T>>>(p, in, out2, ng, L); }); \
         report("TILE " #TR "x" #TC " halves" #NH " t" #T " minb" #MB, ms); }
+    if (argc > 2 && atoi(argv[2]) == 4) {
+        double* gtab; cudaMalloc(&gtab, kGI * kGS * 8);
+        { std::vector<double> t(kGI * kGS); for (int i = 0; i < kGI * kGS; ++i) t[i] = 0.01 * cos(0.1 * i); cudaMemcpy(gtab, t.data(), t.size() * 8, cudaMemcpyHostToDevice); }
+        double* dout; cudaMalloc(&dout, n * 8);
+        const size_t gsm = kGI * kGS * 8;
+#define RUNFD(MB) { int ng = B * V / 2; float ms = time_it([&] { k_fwd_direct<MB><<<(ng + 127) / 128, 128, gsm>>>(p, in, out, dout, gtab, ng, L); }); report("FWD direct rows2 minb" #MB, ms); }
+#define RUNFT(ROWS, NH, MB) { constexpr size_t sm = (3 * (ROWS * 2 + 2) * 64 + kGI * kGS) * 8; \
+        cudaFuncSetAttribute(k_fwd_tile<64, ROWS, NH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        int nb = B * V / (ROWS * 128); float ms = time_it([&] { k_fwd_tile<64, ROWS, NH, MB><<<nb, 128, sm>>>(p, in, out2, dout, gtab); }); \
+        report("FWD tile rows" #ROWS " passes" #NH " minb" #MB, ms); }
+        RUNFD(1) RUNFD(6) RUNFD(5)
+        RUNFT(2, 1, 5) RUNFT(2, 1, 6) RUNFT(2, 1, 4) RUNFT(4, 2, 4) RUNFT(4, 2, 5) RUNFT(4, 2, 6) RUNFT(4, 2, 3) RUNFT(2, 2, 6) RUNFT(2, 2, 8)
+        { int ng = B * V / 2; k_fwd_direct<1><<<(ng + 127) / 128, 128, gsm>>>(p, in, out, dout, gtab, ng, L); constexpr size_t sm = (3 * 10 * 64 + kGI * kGS) * 8; k_fwd_tile<64, 4, 2, 4><<<B * V / 512, 128, sm>>>(p, in, out2, dout, gtab); }
+        std::vector<double> a(n), b2(n);
+        cudaMemcpy(a.data(), out, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b2.data(), out2, n * 8, cudaMemcpyDeviceToHost);
+        double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs(a[i] - b2[i]));
+        printf("max diff fwd tile vs direct %.3e (%s)\n", md, cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     if (argc > 2 && atoi(argv[2]) == 5) {
         RUN(2, 2, 128, 1)
 #define RUNC(ROWS, ST, T, MB) { int ng = B * V / ROWS; float ms = time_it([&] { k_conv_cpasync<64, ROWS, ST, T, MB><<<ng / T, T>>>(p, in, out2, ng, L); }); \
