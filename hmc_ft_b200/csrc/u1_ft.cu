@@ -180,7 +180,7 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 constexpr int kTileStages = 3;
 
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? 4 : 5))
+__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? 4 : 6))
 k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
             const double* __restrict__ add, const double* __restrict__ mul,
             double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
