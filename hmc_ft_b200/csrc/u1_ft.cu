@@ -952,17 +952,18 @@ static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const do
     return e == cudaSuccess ? U1_OK : (int)e;
 }
 
-static int tile_path_enabled() {          // U1FT_TILE: 0 off, 1 reverse layers only (default), 2 all layers
+static int tile_path_enabled() {          // U1FT_TILE: 0 off, 1 reverse layers only, 2 all layers (default)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("U1FT_TILE"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("U1FT_TILE"); v = e ? atoi(e) : 2; }
     return v;
 }
 
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
-    // Measured in the full force (342 chains, ncu launch list): the tiled kernel wins for the reverse
-    // layers (135 vs 161 us) but loses for the forward+GELU layers (298 vs 228 us), so only EPI_BWD uses it.
+    // Measured in the full force (342 chains): reverse layers 135 vs 161 us (ncu), whole force 22.0 vs
+    // 19.8 TFLOP/s with both directions tiled.  The forward variant needs the 80-register cap
+    // (__launch_bounds__ minBlocks 6): at 96 registers ptxas schedules it 30 % slower than the direct kernel.
     if (tile_path_enabled() && (EPI == EPI_BWD || tile_path_enabled() > 1)) {
         if (L == 64) return launch_conv_tile<64, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
         if (L == 32) return launch_conv_tile<32, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
