@@ -38,12 +38,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    extra = os.environ.get("U1_NVCC_DEFINES", "").split()        # e.g. "-DU1_TILE_FWD_MINB=7" (tuning runs)
     objs = []
     procs = []
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s).replace(".cu", ".o"))
         objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for cmd, p in procs:

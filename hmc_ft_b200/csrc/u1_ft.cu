@@ -178,9 +178,15 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 // layers ROWS=4.  Same epilogues and launch protocol as k_conv.
 // ---------------------------------------------------------------------------------------
 constexpr int kTileStages = 3;
+#ifndef U1_TILE_FWD_MINB
+#define U1_TILE_FWD_MINB 6
+#endif
+#ifndef U1_TILE_BWD_MINB
+#define U1_TILE_BWD_MINB 4
+#endif
 
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? 4 : 6))
+__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))
 k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
             const double* __restrict__ add, const double* __restrict__ mul,
             double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
