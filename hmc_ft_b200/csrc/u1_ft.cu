@@ -36,29 +36,30 @@ enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
 
 // ---------------------------------------------------------------------------------------
 // exact-erf GELU (nn.GELU default, a = z*Phi(z)) and its derivative (Phi + z*phi) from a piecewise
-// Taylor table of Phi held in shared memory: 136 intervals of width 1/8 on [-8.5, 8.5], degree 11
+// Taylor table of Phi held in shared memory: 137 intervals of width 1/8 centred on i/8, |i| <= 68, degree 11
 // (truncation < 2e-20 for Phi, < 4e-18 for phi = Phi'), evaluated by one Horner pass that carries
 // the derivative: 22 DFMA + 12 LDS per value instead of the ~135 instruction slots of
 // erf() + exp().  The table is built in 80-bit arithmetic at handle creation (build_gelu_table).
 // ---------------------------------------------------------------------------------------
-constexpr int kGeluIntervals = 136, kGeluDeg = 11, kGeluStride = 13;   // odd stride: conflict-free banks
+constexpr int kGeluIntervals = 137, kGeluDeg = 11, kGeluStride = 13;   // odd stride: conflict-free banks
 constexpr double kGeluZmax = 8.5, kGeluInvH = 8.0;
 constexpr int kGeluTableDoubles = kGeluIntervals * kGeluStride;
 
+// Interval i is centred at i/8 (i = -68..68, row i+68 of the table); i = rint(8 z) comes for free from
+// the low word of 8z + 1.5*2^52.  |z| > 8.5 is clamped: Phi(-8.5) = 9.5e-18, phi(8.5) = 8e-17.
 __device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, double z, double& a, double& d) {
-    const double zc = fmin(fmax(z, -kGeluZmax), kGeluZmax - 1e-9);
-    const int i = __double2int_rd((zc + kGeluZmax) * kGeluInvH);
-    const double t = zc - (((double)i + 0.5) * (1.0 / kGeluInvH) - kGeluZmax);
-    const double* q = tab + i * kGeluStride;
+    constexpr double kMagic = 6755399441055744.0;
+    const double zc = fmin(fmax(z, -kGeluZmax), kGeluZmax);
+    const double m = fma(zc, kGeluInvH, kMagic);
+    const int i = __double2loint(m);
+    const double t = fma(m - kMagic, -1.0 / kGeluInvH, zc);
+    const double* q = tab + (i + 68) * kGeluStride;
     double p = q[kGeluDeg], dp = 0.0;
 #pragma unroll
     for (int k = kGeluDeg - 1; k >= 0; --k) {
         dp = fma(dp, t, p);
         p = fma(p, t, q[k]);
     }
-    const bool lo = z < -kGeluZmax, hi = z > kGeluZmax;
-    p = lo ? 0.0 : (hi ? 1.0 : p);
-    dp = (lo || hi) ? 0.0 : dp;
     a = z * p;
     d = fma(z, dp, p);
 }
@@ -66,7 +67,7 @@ __device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, do
 static void build_gelu_table(double* out) {
     const long double sqrt2pi = sqrtl(2.0L * acosl(-1.0L));
     for (int i = 0; i < kGeluIntervals; ++i) {
-        const long double c = -(long double)kGeluZmax + ((long double)i + 0.5L) / (long double)kGeluInvH;
+        const long double c = ((long double)i - 68.0L) / (long double)kGeluInvH;
         const long double phi = expl(-0.5L * c * c) / sqrt2pi;
         long double he_prev = 0.0L, he = 1.0L;          // He_{-1} := 0, He_0 = 1
         long double fact = 1.0L, sign = 1.0L;
