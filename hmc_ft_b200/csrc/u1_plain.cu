@@ -252,6 +252,187 @@ static int launch_step(const StepArgs& in, int B, bool slab, cudaStream_t st) {
     return U1_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Temporally blocked leapfrog for lattices that do not fit one SM (L > 64, slabs): a CTA loads a
+// 64 x 64 window of (theta, pi) into registers exactly like k_traj_resident, advances it `ksteps`
+// (<= 4) leapfrog steps treating the window as periodic, and writes back only the inner 56 x 56
+// sites.  The wrap-around contaminates one ring of sites per step, which never reaches the inner
+// block, so the result is bit-identical to `ksteps` launches of k_leapfrog_step while HBM is
+// touched once per 4 steps: algorithmic traffic 64 B per site-update, real traffic
+// (64^2 + 56^2)/(56^2 * 4) * 32 B = 18.4 B.  Needs L % 4 == 0 (16-byte aligned thread tiles).
+// ---------------------------------------------------------------------------------------
+constexpr int kMsE = 64, kMsHalo = 4, kMsOut = kMsE - 2 * kMsHalo;   // window side, halo, inner block side
+
+struct MultiArgs {
+    const double* th; const double* pi;
+    double* tho; double* pio;
+    int Lx, L, tiles_y, ksteps;
+    double beta, first_drift, dt;
+};
+
+__global__ void __launch_bounds__(512)
+k_leapfrog_multi(MultiArgs a) {
+    constexpr int L = kMsE, TX = 2, TY = 4, NTX = L / TX, NTY = L / TY;
+    extern __shared__ double dsm[];
+    double* colA = dsm;
+    double* rowA = colA + L * NTY;
+    double* colB = rowA + NTX * TY * NTY;
+    double* rowB = colB + L * NTY;
+
+    const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
+    const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
+    const int tile_x = blockIdx.x / a.tiles_y, tile_y = blockIdx.x - tile_x * a.tiles_y;
+    const size_t V = (size_t)a.Lx * a.L;
+    const size_t base = (size_t)blockIdx.y * 2 * V;
+    // global coordinates of this thread's 2 x 4 sites (periodic)
+    int gy = tile_y * kMsOut - kMsHalo + y0;
+    gy %= a.L; if (gy < 0) gy += a.L;
+    int gx[TX];
+#pragma unroll
+    for (int i = 0; i < TX; ++i) { int g = (tile_x * kMsOut - kMsHalo + x0 + i) % a.Lx; gx[i] = g < 0 ? g + a.Lx : g; }
+
+    double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
+#pragma unroll
+    for (int i = 0; i < TX; ++i)
+#pragma unroll
+        for (int j = 0; j < TY; j += 2) {
+            const size_t g = base + (size_t)gx[i] * a.L + gy + j;
+            const double2 v0 = *reinterpret_cast<const double2*>(a.th + g);
+            const double2 v1 = *reinterpret_cast<const double2*>(a.th + g + V);
+            const double2 q0 = *reinterpret_cast<const double2*>(a.pi + g);
+            const double2 q1 = *reinterpret_cast<const double2*>(a.pi + g + V);
+            th0[i][j] = v0.x; th0[i][j + 1] = v0.y; th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
+            p0[i][j] = q0.x; p0[i][j + 1] = q0.y; p1[i][j] = q1.x; p1[i][j + 1] = q1.y;
+        }
+    const double kb = a.dt * a.beta;
+    for (int s = 0; s < a.ksteps; ++s) {
+        const double dr = (s == 0) ? a.first_drift : a.dt;
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; ++j) {
+                th0[i][j] = fma(dr, p0[i][j], th0[i][j]);
+                th1[i][j] = fma(dr, p1[i][j], th1[i][j]);
+            }
+#pragma unroll
+        for (int i = 0; i < TX; ++i) colA[(x0 + i) * NTY + ty] = th0[i][0];
+#pragma unroll
+        for (int j = 0; j < TY; ++j) rowA[(tx * TY + j) * NTY + ty] = th1[0][j];
+        __syncthreads();
+        double S[TX][TY];
+        {
+            double rc[TX], rr[TY];
+#pragma unroll
+            for (int i = 0; i < TX; ++i) rc[i] = colA[(x0 + i) * NTY + tyR];
+#pragma unroll
+            for (int j = 0; j < TY; ++j) rr[j] = rowA[(txD * TY + j) * NTY + ty];
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int j = 0; j < TY; ++j) {
+                    const double right = (j + 1 < TY) ? th0[i][j + 1] : rc[i];
+                    const double down = (i + 1 < TX) ? th1[i + 1][j] : rr[j];
+                    S[i][j] = fast_sin(th0[i][j] - th1[i][j] - right + down);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < TX; ++i) colB[(x0 + i) * NTY + ty] = S[i][TY - 1];
+#pragma unroll
+        for (int j = 0; j < TY; ++j) rowB[(tx * TY + j) * NTY + ty] = S[TX - 1][j];
+        __syncthreads();
+        double lc[TX], ur[TY];
+#pragma unroll
+        for (int i = 0; i < TX; ++i) lc[i] = colB[(x0 + i) * NTY + tyL];
+#pragma unroll
+        for (int j = 0; j < TY; ++j) ur[j] = rowB[(txU * TY + j) * NTY + ty];
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int j = 0; j < TY; ++j) {
+                const double left = (j > 0) ? S[i][j - 1] : lc[i];
+                const double up = (i > 0) ? S[i - 1][j] : ur[j];
+                p0[i][j] = fma(-kb, S[i][j] - left, p0[i][j]);
+                p1[i][j] = fma(-kb, up - S[i][j], p1[i][j]);
+            }
+    }
+    // write back the inner block (clipped to the lattice for the last tile row / column)
+    const int ly = y0 - kMsHalo;                       // column inside the inner block (multiple of 4)
+    if (ly < 0 || ly >= kMsOut || tile_y * kMsOut + ly >= a.L) return;
+#pragma unroll
+    for (int i = 0; i < TX; ++i) {
+        const int lx = x0 + i - kMsHalo;
+        if (lx < 0 || lx >= kMsOut || tile_x * kMsOut + lx >= a.Lx) continue;
+#pragma unroll
+        for (int j = 0; j < TY; j += 2) {
+            const size_t g = base + (size_t)gx[i] * a.L + gy + j;
+            *reinterpret_cast<double2*>(a.tho + g) = make_double2(th0[i][j], th0[i][j + 1]);
+            *reinterpret_cast<double2*>(a.tho + g + V) = make_double2(th1[i][j], th1[i][j + 1]);
+            *reinterpret_cast<double2*>(a.pio + g) = make_double2(p0[i][j], p0[i][j + 1]);
+            *reinterpret_cast<double2*>(a.pio + g + V) = make_double2(p1[i][j], p1[i][j + 1]);
+        }
+    }
+}
+
+static bool multi_supported(int Lx, int L) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("U1_MULTISTEP"); enabled = e ? atoi(e) : 1; }
+    return enabled && (L % 4 == 0) && Lx >= kMsE && L >= kMsE;
+}
+
+static int launch_multi(const double* th, const double* pi, double* tho, double* pio, int B, int Lx, int L,
+                        double beta, double first_drift, double dt, int ksteps, cudaStream_t st) {
+    MultiArgs a{};
+    a.th = th; a.pi = pi; a.tho = tho; a.pio = pio;
+    a.Lx = Lx; a.L = L; a.ksteps = ksteps; a.beta = beta; a.first_drift = first_drift; a.dt = dt;
+    const int tiles_x = (Lx + kMsOut - 1) / kMsOut;
+    a.tiles_y = (L + kMsOut - 1) / kMsOut;
+    constexpr int NTX = kMsE / 2, NTY = kMsE / 4;
+    constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_leapfrog_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    k_leapfrog_multi<<<dim3(tiles_x * a.tiles_y, B), 512, smem, st>>>(a);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+// n leapfrog steps (first drift `first_drift`, then dt) ping-ponging between (thA,piA) and (thB,piB),
+// starting from `th_in/pi_in` (which may be a third buffer).  Uses the temporally blocked kernel in
+// groups of up to 4 steps when the lattice allows it.  Returns the buffers holding the result.
+static int leapfrog_steps(const double* th_in, const double* pi_in, double* thA, double* piA, double* thB,
+                          double* piB, int B, int Lx, int L, double beta, double first_drift, double dt, int n,
+                          cudaStream_t st, const double** th_res, const double** pi_res) {
+    const double* ct = th_in;
+    const double* cp = pi_in;
+    const bool multi = multi_supported(Lx, L);
+    int done = 0, launch = 0;
+    while (done < n) {
+        const int k = multi ? ((n - done) < kMsHalo ? (n - done) : kMsHalo) : 1;
+        double* ot = (ct == thA) ? thB : thA;
+        double* op = (ct == thA) ? piB : piA;
+        const double fd = (done == 0) ? first_drift : dt;
+        if (multi) {
+            U1_TRY(launch_multi(ct, cp, ot, op, B, Lx, L, beta, fd, dt, k, st));
+        } else {
+            StepArgs a{};
+            a.th = ct; a.pi = cp; a.tho = ot; a.pio = op;
+            a.Lx = Lx; a.L = L; a.beta = beta; a.drift = fd; a.kick = dt;
+            U1_TRY(launch_step(a, B, false, st));
+        }
+        ct = ot; cp = op;
+        done += k; ++launch;
+    }
+    *th_res = ct; *pi_res = cp;
+    return U1_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Per-chain sums: [0]=sum cos(wrap P), [1]=sum wrap P, [2]=sum pi^2.  Two deterministic phases.
 // ---------------------------------------------------------------------------------------
@@ -825,17 +1006,15 @@ int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* t
 
 int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
                            int B, int Lx, int L, double beta, double first_drift, double dt, int n,
-                           u1_stream_t stream) {
+                           int* result_in_B, u1_stream_t stream) {
     g_launches = 0;
-    if (!thetaA || !piA || !thetaB || !piB || B <= 0 || L <= 0 || Lx <= 0 || n < 0) return U1_ERR_ARG;
+    if (!thetaA || !piA || !thetaB || !piB || !result_in_B || B <= 0 || L <= 0 || Lx <= 0 || n < 0) return U1_ERR_ARG;
     if (thetaA == thetaB || piA == piB) return U1_ERR_ARG;
-    for (int s = 0; s < n; ++s) {
-        StepArgs a{};
-        a.th = (s & 1) ? thetaB : thetaA; a.pi = (s & 1) ? piB : piA;
-        a.tho = (s & 1) ? thetaA : thetaB; a.pio = (s & 1) ? piA : piB;
-        a.Lx = Lx; a.L = L; a.beta = beta; a.drift = (s == 0) ? first_drift : dt; a.kick = dt;
-        U1_TRY(launch_step(a, B, false, (cudaStream_t)stream));
-    }
+    const double *ct = thetaA, *cp = piA;
+    if (n > 0)
+        U1_TRY(leapfrog_steps(thetaA, piA, thetaA, piA, thetaB, piB, B, Lx, L, beta, first_drift, dt, n,
+                              (cudaStream_t)stream, &ct, &cp));
+    *result_in_B = (ct == thetaB) ? 1 : 0;
     return U1_OK;
 }
 
@@ -853,19 +1032,8 @@ int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
 static int leapfrog_stream(const double* th_in, const double* pi_in, PlainWs& w, int B, int L,
                            double beta, double dt, int n_steps, cudaStream_t st,
                            const double** th_res, const double** pi_res) {
-    const double* ct = th_in;
-    const double* cp = pi_in;
-    for (int s = 0; s < n_steps; ++s) {
-        double* ot = (s & 1) ? w.thB : w.thA;
-        double* op = (s & 1) ? w.piB : w.piA;
-        StepArgs a{};
-        a.th = ct; a.pi = cp; a.tho = ot; a.pio = op;
-        a.Lx = L; a.L = L; a.beta = beta; a.drift = (s == 0) ? 0.5 * dt : dt; a.kick = dt;
-        U1_TRY(launch_step(a, B, false, st));
-        ct = ot; cp = op;
-    }
-    *th_res = ct; *pi_res = cp;
-    return U1_OK;
+    return leapfrog_steps(th_in, pi_in, w.thA, w.piA, w.thB, w.piB, B, L, L, beta, 0.5 * dt, dt, n_steps, st,
+                          th_res, pi_res);
 }
 
 int u1_leapfrog(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,

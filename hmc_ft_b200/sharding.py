@@ -12,6 +12,7 @@
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Dict, Optional, Tuple
 
@@ -164,11 +165,12 @@ class SlabHMC:
                 if done > 0:
                     self.halo.exchange(cur)                  # theta and pi, k rows each side
                 nb = min(k, self.n_steps - done)
+                in_b = C.c_int(0)
                 self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
                                                       nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
-                                                      0.5 * dt if done == 0 else dt, dt, nb, sp),
+                                                      0.5 * dt if done == 0 else dt, dt, nb, C.byref(in_b), sp),
                            "u1_leapfrog_steps_rect")
-                if nb & 1:
+                if in_b.value:
                     cur, nxt = nxt, cur
                 done += nb
             # final half drift + wrap on own rows (hmc_u1.py:78-79), then H_new

@@ -123,12 +123,15 @@ int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
 int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
                           int B, int Lx, int L, double beta, double drift, double kick,
                           u1_stream_t stream);
-/* n consecutive steps of the rectangular kernel in one call, ping-ponging between (thetaA,piA) and
- * (thetaB,piB): step 0 reads A and writes B, step 1 reads B and writes A, ...  The first step drifts by
- * first_drift, the others by dt; every kick is dt.  The result is in A if n is even, in B if odd. */
+/* n consecutive leapfrog steps of a periodic Lx x L lattice in one call, ping-ponging between
+ * (thetaA,piA) (the input) and (thetaB,piB).  The first step drifts by first_drift, the others by dt;
+ * every kick is dt.  When L % 4 == 0 and Lx, L >= 64 the steps run in groups of up to four inside the
+ * temporally blocked kernel (64 x 64 register-resident windows, one HBM pass per group; bit-identical
+ * to single steps), otherwise one k_leapfrog_step launch per step.  *result_in_B (host int) tells
+ * which buffer pair holds the result. */
 int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
                            int B, int Lx, int L, double beta, double first_drift, double dt, int n,
-                           u1_stream_t stream);
+                           int* result_in_B, u1_stream_t stream);
 /* Philox momenta for rows x_first .. x_first+Lx-1 (taken modulo Lx_global) of ONE global lattice of
  * Lx_global x L sites: pi[2][Lx][L].  Keyed by the global site index, so the field does not depend
  * on the decomposition. */

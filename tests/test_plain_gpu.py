@@ -51,7 +51,8 @@ def test_golden_action_force_leapfrog(hb, golden_dir, tag):
 
 
 @pytest.mark.parametrize("L,B,path", [(8, 5, 2), (16, 3, 2), (32, 4, 2), (64, 3, 2), (64, 3, 1),
-                                      (16, 2, 1), (6, 3, 1), (12, 2, 1), (130, 1, 1)])
+                                      (16, 2, 1), (6, 3, 1), (12, 2, 1), (130, 1, 1), (128, 2, 1), (100, 1, 1),
+                                      (232, 1, 1)])
 def test_trajectory_vs_oracle(hb, L, B, path):
     """Fused trajectory (both kernel paths) with injected pi/u against the oracle:
     dH, accept, H, plaq, topo, final state."""
@@ -258,3 +259,28 @@ def test_autocorrelation_device(hb, golden_dir):
     assert rel(d, z["auto_by_def"]) < 1e-12 and torch.all(d[:, 3] == 1.0)        # frozen chain -> all ones
     one = U.auto_from_chi(topo[:, 0], ml, beta, vol)                              # numpy in -> numpy out
     assert isinstance(one, np.ndarray) and one.shape == (ml + 1,) and rel(one, z["auto_from_chi"][:, 0]) < 1e-14
+
+
+def test_multistep_kernel_bit_identical_to_single_steps(hb):
+    """u1_leapfrog_steps_rect (temporally blocked, groups of 4 steps) == repeated u1_leapfrog_step,
+    bit for bit, on a rectangular periodic lattice whose sides are not multiples of the 56-site block."""
+    import ctypes as C
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    Lx, L, B, n, beta, dt = 72, 100, 2, 7, 3.0, 0.07
+    g = torch.Generator().manual_seed(77)
+    th = ((torch.rand(B, 2, Lx, L, generator=g, dtype=torch.float64) * 2 - 1) * 3).cuda()
+    pi = torch.randn(B, 2, Lx, L, generator=g, dtype=torch.float64).cuda()
+    sp = torch.cuda.current_stream().cuda_stream
+    a_t, a_p, b_t, b_p = th.clone(), pi.clone(), torch.empty_like(th), torch.empty_like(pi)
+    flag = C.c_int(0)
+    _lib.check(lib.u1_leapfrog_steps_rect(a_t.data_ptr(), a_p.data_ptr(), b_t.data_ptr(), b_p.data_ptr(), B, Lx, L,
+                                          beta, 0.5 * dt, dt, n, C.byref(flag), sp))
+    res_t, res_p = (b_t, b_p) if flag.value else (a_t, a_p)
+    c_t, c_p, d_t, d_p = th.clone(), pi.clone(), torch.empty_like(th), torch.empty_like(pi)
+    for s in range(n):
+        _lib.check(lib.u1_leapfrog_step_rect(c_t.data_ptr(), c_p.data_ptr(), d_t.data_ptr(), d_p.data_ptr(), B, Lx, L,
+                                             beta, 0.5 * dt if s == 0 else dt, dt, sp))
+        c_t, d_t, c_p, d_p = d_t, c_t, d_p, c_p
+    torch.cuda.synchronize()
+    assert torch.equal(res_t, c_t) and torch.equal(res_p, c_p)
