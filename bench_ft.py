@@ -74,10 +74,27 @@ def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50,
     outs = []
     ms = time_steps(lambda: outs.append(slab.trajectory(own)), steps, warmup, world)
     su = L * L * n_steps / (ms * 1e-3)
+    # the temporally blocked step kernel alone (4 leapfrog steps per launch) on this rank's extended slab
+    import ctypes as C
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    cur, nxt = slab._ext
+    flag = C.c_int(0)
+    sp = torch.cuda.current_stream().cuda_stream
+    rows = cur.shape[2]
+
+    def four_steps():
+        _lib.check(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(), nxt[1].data_ptr(),
+                                              1, rows, L, beta, dt, dt, 4, C.byref(flag), sp))
+    ms4 = time_steps(four_steps, 10, 3, 1)
+    su4 = rows * L * 4 / (ms4 * 1e-3)
     return {"metric": f"site-updates/s, single lattice L={L} plain HMC, slab-decomposed over {world} GPU(s), "
                       f"halo {slab.k} rows exchanged every {slab.k} steps",
             "value": su, "unit": "site-updates/s", "ms_per_step": ms, "scaling": "strong",
             "rows_per_gpu": slab.Lx, "halo_exchanges_per_trajectory": slab.halo.n_exchanges // (steps + warmup),
             "halo_bytes_sent_per_trajectory_per_gpu": slab.halo.bytes_sent // (steps + warmup),
             "gpu_launches_per_step": slab.gpu_launches // (steps + warmup),
-            "hbm_frac_of_measured_peak_per_gpu": None}
+            "hbm_frac_of_measured_peak_per_gpu": None,
+            "multistep_kernel": {"kernel": "k_leapfrog_multi (4 steps per launch)", "site_updates_per_s_per_gpu": su4,
+                                 "algorithmic_GBps": su4 * 64 / 1e9, "ms_per_launch": ms4,
+                                 "real_dram_bytes_per_site_update": 32.0 * (64 * 64 + 56 * 56) / (56 * 56 * 4)}}
