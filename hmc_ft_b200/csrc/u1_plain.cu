@@ -262,7 +262,7 @@ static int launch_step(const StepArgs& in, int B, bool slab, cudaStream_t st) {
 // touched once per 4 steps: algorithmic traffic 64 B per site-update, real traffic
 // (64^2 + 56^2)/(56^2 * 4) * 32 B = 18.4 B.  Needs L % 4 == 0 (16-byte aligned thread tiles).
 // ---------------------------------------------------------------------------------------
-constexpr int kMsE = 64, kMsHalo = 4, kMsOut = kMsE - 2 * kMsHalo;   // window side, halo, inner block side
+constexpr int kMsE = 64, kMsHalo = 4, kMsOut = kMsE - 2 * kMsHalo;   // window rows, halo, inner block rows
 
 struct MultiArgs {
     const double* th; const double* pi;
@@ -271,9 +271,10 @@ struct MultiArgs {
     double beta, first_drift, dt;
 };
 
-__global__ void __launch_bounds__(512)
+template <int EW>      // window columns (64: one 512-thread CTA per SM; 32: two 256-thread CTAs per SM overlap their phases)
+__global__ void __launch_bounds__((kMsE / 2) * (EW / 4), 512 / ((kMsE / 2) * (EW / 4)))
 k_leapfrog_multi(MultiArgs a) {
-    constexpr int L = kMsE, TX = 2, TY = 4, NTX = L / TX, NTY = L / TY;
+    constexpr int L = kMsE, TX = 2, TY = 4, NTX = L / TX, NTY = EW / TY, OW = EW - 2 * kMsHalo;
     extern __shared__ double dsm[];
     double* colA = dsm;
     double* rowA = colA + L * NTY;
@@ -288,7 +289,7 @@ k_leapfrog_multi(MultiArgs a) {
     const size_t V = (size_t)a.Lx * a.L;
     const size_t base = (size_t)blockIdx.y * 2 * V;
     // global coordinates of this thread's 2 x 4 sites (periodic)
-    int gy = tile_y * kMsOut - kMsHalo + y0;
+    int gy = tile_y * OW - kMsHalo + y0;
     gy %= a.L; if (gy < 0) gy += a.L;
     int gx[TX];
 #pragma unroll
@@ -360,7 +361,7 @@ k_leapfrog_multi(MultiArgs a) {
     }
     // write back the inner block (clipped to the lattice for the last tile row / column)
     const int ly = y0 - kMsHalo;                       // column inside the inner block (multiple of 4)
-    if (ly < 0 || ly >= kMsOut || tile_y * kMsOut + ly >= a.L) return;
+    if (ly < 0 || ly >= OW || tile_y * OW + ly >= a.L) return;
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
         const int lx = x0 + i - kMsHalo;
@@ -387,17 +388,27 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
     MultiArgs a{};
     a.th = th; a.pi = pi; a.tho = tho; a.pio = pio;
     a.Lx = Lx; a.L = L; a.ksteps = ksteps; a.beta = beta; a.first_drift = first_drift; a.dt = dt;
+    static int ew = 0;
+    if (ew == 0) { const char* e = getenv("U1_MULTISTEP_EW"); ew = (e && atoi(e) == 64) ? 64 : 32; }
     const int tiles_x = (Lx + kMsOut - 1) / kMsOut;
-    a.tiles_y = (L + kMsOut - 1) / kMsOut;
-    constexpr int NTX = kMsE / 2, NTY = kMsE / 4;
-    constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_leapfrog_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
+    constexpr int NTX = kMsE / 2;
+    if (ew == 64) {
+        constexpr int NTY = 16;
+        constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
+        a.tiles_y = (L + 56 - 1) / 56;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_leapfrog_multi<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            configured = true;
+        }
+        k_leapfrog_multi<64><<<dim3(tiles_x * a.tiles_y, B), 512, smem, st>>>(a);
+    } else {
+        constexpr int NTY = 8;
+        constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
+        a.tiles_y = (L + 24 - 1) / 24;
+        k_leapfrog_multi<32><<<dim3(tiles_x * a.tiles_y, B), 256, smem, st>>>(a);
     }
-    k_leapfrog_multi<<<dim3(tiles_x * a.tiles_y, B), 512, smem, st>>>(a);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
