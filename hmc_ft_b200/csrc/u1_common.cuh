@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/u1hmc.h"
+#include "u1_fastmath.cuh"
 
 namespace u1 {
 
@@ -98,15 +99,23 @@ __host__ __device__ __forceinline__ PhiloxKey chain_key(uint64_t seed, uint64_t 
     return k;
 }
 
-// Momenta of lattice site s (= x*L+y) for (seed, chain, traj): Box-Muller pair -> (pi0, pi1).
+// Table of u1::neg2_log (tools/gen_log_table.py): static constant data, one copy per translation unit.
+static __device__ const LogTabEntry kLogTab[kLogTabN] = {
+#include "u1_logtab.inc"
+};
+
+// Momenta of lattice site s (= x*L+y) for (seed, chain, traj): Box-Muller pair -> (pi0, pi1) =
+// sqrt(-2 ln u1) (cos, sin)(2 pi u2).  Built from the branch-free helpers of u1_fastmath.cuh (about a
+// third of the instructions of log()+sqrt()+sincos(); same values to a few 1e-16).  `tab` is kLogTab
+// or a shared-memory copy of it.  The 1e-300 keeps u1 == 1 (probability 2^-53) finite.
 __device__ __forceinline__ void philox_site_normals(PhiloxKey k, uint64_t traj, uint32_t site,
-                                                    double& n0, double& n1) {
+                                                    const LogTabEntry* __restrict__ tab, double& n0, double& n1) {
     U4 c{site, (uint32_t)traj, (uint32_t)(traj >> 32), 0u};
     U4 r = philox4x32_10(c, k.k0, k.k1);
     const double u1v = u01_53(r.x, r.y), u2v = u01_53(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1v));
+    const double rad = sqrt_pos(neg2_log(u1v, tab) + 1e-300);
     double s, co;
-    sincos(kTwoPi * u2v, &s, &co);
+    fast_sincos(kTwoPi * u2v, s, co);
     n0 = rad * co;
     n1 = rad * s;
 }

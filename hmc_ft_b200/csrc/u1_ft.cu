@@ -36,17 +36,31 @@ enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
 
 // ---------------------------------------------------------------------------------------
 // exact-erf GELU (nn.GELU default, a = z*Phi(z)) and its derivative (Phi + z*phi) from a piecewise
-// Taylor table of Phi held in shared memory: 137 intervals of width 1/8 centred on i/8, |i| <= 68, degree 11
-// (truncation < 2e-20 for Phi, < 4e-18 for phi = Phi'), evaluated by one Horner pass that carries
-// the derivative: 22 DFMA + 12 LDS per value instead of the ~135 instruction slots of
-// erf() + exp().  The table is built in 80-bit arithmetic at handle creation (build_gelu_table).
+// Taylor table held in shared memory, evaluated by one Horner pass that carries the derivative.
+// The table is built in 80-bit arithmetic at handle creation (build_gelu_table).
+//   U1_GELU_V == 1: table of Phi on [-8.5, 8.5], 137 intervals of width 1/8, degree 11
+//                   (truncation < 2e-20 for Phi, < 4e-18 for phi): 22 DFMA + 12 LDS per value.
+//   U1_GELU_V == 2: table of the odd part Psi = Phi - 1/2 on [0, 8.5] only (Phi(z) = 1/2 + sgn(z) Psi(|z|),
+//                   phi even): 137 intervals of width 1/16, degree 9 (truncation < 1e-18 for Psi,
+//                   < 3e-17 for phi): 17 DFMA + 10 LDS per value, |z| and the clamp done on the integer
+//                   pipe (no fmin/fmax), absolute accuracy like 0.5*(1+erf) itself.
+// |z| > 8.5 is clamped: Phi(-8.5) = 9.5e-18, phi(8.5) = 8e-17.
 // ---------------------------------------------------------------------------------------
+#ifndef U1_GELU_V
+#define U1_GELU_V 2
+#endif
+#if U1_GELU_V == 1
 constexpr int kGeluIntervals = 137, kGeluDeg = 11, kGeluStride = 13;   // odd stride: conflict-free banks
 constexpr double kGeluZmax = 8.5, kGeluInvH = 8.0;
+#else
+constexpr int kGeluIntervals = 137, kGeluDeg = 9, kGeluStride = 11;
+constexpr double kGeluZmax = 8.5, kGeluInvH = 16.0;
+#endif
 constexpr int kGeluTableDoubles = kGeluIntervals * kGeluStride;
 
+#if U1_GELU_V == 1
 // Interval i is centred at i/8 (i = -68..68, row i+68 of the table); i = rint(8 z) comes for free from
-// the low word of 8z + 1.5*2^52.  |z| > 8.5 is clamped: Phi(-8.5) = 9.5e-18, phi(8.5) = 8e-17.
+// the low word of 8z + 1.5*2^52.
 __device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, double z, double& a, double& d) {
     constexpr double kMagic = 6755399441055744.0;
     const double zc = fmin(fmax(z, -kGeluZmax), kGeluZmax);
@@ -81,6 +95,53 @@ static void build_gelu_table(double* out) {
         for (int k = kGeluDeg + 1; k < kGeluStride; ++k) out[i * kGeluStride + k] = 0.0;
     }
 }
+#else
+// Interval i is centred at i/16 (i = 0..136); i = rint(16 |z|) is the low word of 16|z| + 1.5*2^52.
+// |z| is clamped to 8.5 by an unsigned min on the high word (doubles >= 0 order like their bit patterns).
+__device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, double z, double& a, double& d) {
+    constexpr double kMagic = 6755399441055744.0;
+    constexpr unsigned kHiMax = 0x40210000u;             // high word of 8.5
+    const unsigned zh = (unsigned)__double2hiint(z);
+    const unsigned ah = zh & 0x7fffffffu;
+    const bool big = ah >= kHiMax;
+    const double az = __hiloint2double((int)(big ? kHiMax : ah), big ? 0 : __double2loint(z));
+    const double m = fma(az, kGeluInvH, kMagic);
+    const int i = __double2loint(m);
+    const double t = fma(m - kMagic, -1.0 / kGeluInvH, az);
+    const double* q = tab + i * kGeluStride;
+    double p = q[kGeluDeg];
+    double dp = p;
+    p = fma(p, t, q[kGeluDeg - 1]);
+#pragma unroll
+    for (int k = kGeluDeg - 2; k >= 0; --k) {
+        dp = fma(dp, t, p);
+        p = fma(p, t, q[k]);
+    }
+    // p = Psi(|z|), dp = phi(|z|);  Phi(z) = 1/2 + sgn(z) Psi(|z|)
+    const double ps = __hiloint2double(__double2hiint(p) ^ (int)(zh & 0x80000000u), __double2loint(p));
+    const double Phi = 0.5 + ps;
+    a = z * Phi;
+    d = fma(z, dp, Phi);
+}
+
+static void build_gelu_table(double* out) {
+    const long double sqrt2pi = sqrtl(2.0L * acosl(-1.0L));
+    for (int i = 0; i < kGeluIntervals; ++i) {
+        const long double c = (long double)i / (long double)kGeluInvH;
+        const long double phi = expl(-0.5L * c * c) / sqrt2pi;
+        long double he_prev = 0.0L, he = 1.0L;          // He_{-1} := 0, He_0 = 1
+        long double fact = 1.0L, sign = 1.0L;
+        out[i * kGeluStride + 0] = (double)(0.5L * erfl(c / sqrtl(2.0L)));          // Psi(c)
+        for (int k = 1; k <= kGeluDeg; ++k) {            // a_k = (-1)^(k-1) He_{k-1}(c) phi(c) / k!
+            fact *= (long double)k;
+            out[i * kGeluStride + k] = (double)(sign * he * phi / fact);
+            const long double he_next = c * he - (long double)(k - 1) * he_prev;
+            he_prev = he; he = he_next; sign = -sign;
+        }
+        for (int k = kGeluDeg + 1; k < kGeluStride; ++k) out[i * kGeluStride + k] = 0.0;
+    }
+}
+#endif
 
 // out[o](x,y) = sum_{c,i,j} w[c][i*3+j][o] * in[c]((x+i-1)%L, (y+j-1)%L)   (+ epilogue)
 // One thread = two vertically adjacent sites (x, x+1; x even): a 4x3 window per input channel feeds
@@ -180,14 +241,17 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 // ---------------------------------------------------------------------------------------
 constexpr int kTileStages = 3;
 #ifndef U1_TILE_FWD_MINB
-#define U1_TILE_FWD_MINB 6
+#define U1_TILE_FWD_MINB 5
 #endif
 #ifndef U1_TILE_BWD_MINB
 #define U1_TILE_BWD_MINB 4
 #endif
+#ifndef U1_TILE_FWD_ROWS
+#define U1_TILE_FWD_ROWS 2
+#endif
 
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, (ROWS == 4 ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))
+__global__ void __launch_bounds__(kConvThreads, (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))
 k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
             const double* __restrict__ add, const double* __restrict__ mul,
             double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
@@ -223,11 +287,11 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
         }
         asm volatile("cp.async.commit_group;");
     };
-    double acc[ROWS][COUT];
+    double acc[ROWS][COUT];                           // forward layers start from the bias (one DADD less per value)
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[r][o] = 0.0;
+        for (int o = 0; o < COUT; ++o) acc[r][o] = (EPI == EPI_BWD) ? 0.0 : p.b[o];
 #pragma unroll
     for (int st = 0; st < kTileStages - 1; ++st) issue(st, st);
     const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
@@ -270,7 +334,7 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
                 if (mul) rv *= mul[idx];
                 out[idx] = rv;
             } else {
-                double z = acc[r][o] + p.b[o];
+                double z = acc[r][o];
                 if (add) z += add[idx];
                 double g, d;
                 gelu_and_grad(s_tab, z, g, d);
@@ -770,7 +834,7 @@ __global__ void k_momenta_ft(double* __restrict__ pi, uint64_t seed, uint64_t ch
     if (s >= nsites) return;
     const int b = s / V, site = s - b * V;
     double n0, n1;
-    philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, n0, n1);
+    philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, kLogTab, n0, n1);
     pi[(size_t)b * 2 * V + site] = n0;
     pi[(size_t)b * 2 * V + V + site] = n1;
 }
@@ -941,7 +1005,7 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int b
 template <int LL, int CIN, int COUT, int EPI>
 static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                             const double* mul, double* out, double* dout, int nsites, cudaStream_t st) {
-    constexpr int ROWS = (EPI == EPI_BWD) ? 4 : 2;
+    constexpr int ROWS = (EPI == EPI_BWD) ? 4 : U1_TILE_FWD_ROWS;
     constexpr int TILE = (ROWS * (kConvThreads / LL) + 2) * LL;
     constexpr size_t smem = ((size_t)kTileStages * TILE + (EPI == EPI_BWD ? 0 : kGeluTableDoubles)) * sizeof(double);
     static bool configured = false;

@@ -70,7 +70,7 @@ __global__ void k_momenta(double* __restrict__ pi, uint64_t seed, uint64_t chain
          s += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(s / V), site = (int)(s - (long long)b * V);
         double n0, n1;
-        philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, n0, n1);
+        philox_site_normals(chain_key(seed, chain0 + b), traj, (uint32_t)site, kLogTab, n0, n1);
         pi[(size_t)b * 2 * V + site] = n0;
         pi[(size_t)b * 2 * V + V + site] = n1;
     }
@@ -86,7 +86,7 @@ __global__ void k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t 
         long long xg = (x_first + xl) % Lxg;
         if (xg < 0) xg += Lxg;
         double n0, n1;
-        philox_site_normals(key, traj, (uint32_t)(xg * L + y), n0, n1);
+        philox_site_normals(key, traj, (uint32_t)(xg * L + y), kLogTab, n0, n1);
         pi[s] = n0;
         pi[n + s] = n1;
     }
@@ -578,6 +578,7 @@ k_traj_resident(TrajArgs a) {
     double* colB = rowA + NTX * TY * NTY;     // sinP at (x, last column of tile ty)
     double* rowB = colB + L * NTY;            // sinP at (last row of tile tx, y)
     double* red = rowB + NTX * TY * NTY;      // 3*32 reduction scratch
+    LogTabEntry* ltab = reinterpret_cast<LogTabEntry*>(red + 96);   // Box-Muller log table (2 KB)
 
     const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
     const int x0 = tx * TX, y0 = ty * TY;
@@ -590,6 +591,8 @@ k_traj_resident(TrajArgs a) {
     const double beta = a.beta, dt = a.dt, kb = a.dt * a.beta;
 
     double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
+    for (int i = tid; i < kLogTabN; i += NT) ltab[i] = kLogTab[i];
+    __syncthreads();
 
     auto publish_theta = [&]() {
 #pragma unroll
@@ -612,21 +615,25 @@ k_traj_resident(TrajArgs a) {
                 P[i][j] = th0[i][j] - th1[i][j] - right + down;
             }
     };
-    auto hamiltonian_sums = [&](double (&v)[3]) {   // v = {sum cos wrapP, sum wrapP, sum pi^2}
+    // v = {sum cos P, -(sum of plaquette winding numbers) = topological charge, sum pi^2}.  cos(wrap P) =
+    // cos P and sum wrap(P) = -2 pi sum n(P) (utils.py:173-196), so neither the wrap nor cos()'s
+    // general-range reduction is needed: fast_cos + an integer winding count.
+    auto hamiltonian_sums = [&](double (&v)[3]) {
         double P[TX][TY];
         publish_theta();
         __syncthreads();
         plaquettes(P);
-        v[0] = v[1] = v[2] = 0.0;
+        v[0] = v[2] = 0.0;
+        int nw = 0;
 #pragma unroll
         for (int i = 0; i < TX; ++i)
 #pragma unroll
             for (int j = 0; j < TY; ++j) {
-                const double w = wrap_pi(P[i][j]);
-                v[0] += cos(w);
-                v[1] += w;
+                v[0] += fast_cos(P[i][j]);
+                nw += winding(P[i][j]);
                 v[2] += p0[i][j] * p0[i][j] + p1[i][j] * p1[i][j];
             }
+        v[1] = (double)(-nw);
         block_sum<3>(v, red);
     };
 
@@ -658,7 +665,7 @@ k_traj_resident(TrajArgs a) {
             for (int i = 0; i < TX; ++i)
 #pragma unroll
                 for (int j = 0; j < TY; ++j)
-                    philox_site_normals(key, traj, (uint32_t)((x0 + i) * L + y0 + j), p0[i][j], p1[i][j]);
+                    philox_site_normals(key, traj, (uint32_t)((x0 + i) * L + y0 + j), ltab, p0[i][j], p1[i][j]);
         }
         // ---- H_old (hmc_u1.py:84-85) ----
         double so[3];
@@ -707,8 +714,8 @@ k_traj_resident(TrajArgs a) {
         for (int i = 0; i < TX; ++i)
 #pragma unroll
             for (int j = 0; j < TY; ++j) {
-                th0[i][j] = wrap_pi(fma(0.5 * dt, p0[i][j], th0[i][j]));
-                th1[i][j] = wrap_pi(fma(0.5 * dt, p1[i][j], th1[i][j]));
+                th0[i][j] = wrap_fast(fma(0.5 * dt, p0[i][j], th0[i][j]));
+                th1[i][j] = wrap_fast(fma(0.5 * dt, p1[i][j], th1[i][j]));
             }
         // ---- H_new, accept/reject (hmc_u1.py:88-97) ----
         double sn[3];
@@ -734,7 +741,7 @@ k_traj_resident(TrajArgs a) {
             if (a.out_acc) a.out_acc[o] = acc ? 1 : 0;
             if (a.out_H) a.out_H[o] = acc ? H_new : H_old;
             if (a.out_plaq) a.out_plaq[o] = f[0] * (1.0 / V);
-            if (a.out_topo) a.out_topo[o] = floor(0.1 + f[1] / kTwoPi);
+            if (a.out_topo) a.out_topo[o] = f[1];
         }
     }
 }
@@ -796,7 +803,7 @@ static bool resident_supported(int L) { return L == 8 || L == 16 || L == 32 || L
 template <int L, int TX, int TY>
 static int launch_resident_t(const TrajArgs& a, cudaStream_t st) {
     constexpr int NTX = L / TX, NTY = L / TY;
-    constexpr size_t smem = (size_t)(2 * (L * NTY + NTX * TY * NTY) + 3 * 32) * sizeof(double);
+    constexpr size_t smem = (size_t)(2 * (L * NTY + NTX * TY * NTY) + 3 * 32) * sizeof(double) + kLogTabN * sizeof(LogTabEntry);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_traj_resident<L, TX, TY>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
