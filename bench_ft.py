@@ -95,6 +95,7 @@ def bench_slab(args, rank, world, dev, time_steps, L=4096, beta=6.0, n_steps=50,
             "halo_bytes_sent_per_trajectory_per_gpu": slab.halo.bytes_sent // (steps + warmup),
             "gpu_launches_per_step": slab.gpu_launches // (steps + warmup),
             "hbm_frac_of_measured_peak_per_gpu": None,
+            "cuda_graph_replay": slab._graph is not None, "cuda_graph_error": slab.graph_error,
             "multistep_kernel": {"kernel": "k_leapfrog_multi (4 steps per launch)", "site_updates_per_s_per_gpu": su4,
                                  "algorithmic_GBps": su4 * 64 / 1e9, "ms_per_launch": ms4,
                                  "real_dram_bytes_per_site_update": 32.0 * (64 * 64 + 56 * 56) / (56 * 56 * 4)}}

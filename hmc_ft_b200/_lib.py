@@ -35,8 +35,10 @@ SIGNATURES = {
     "u1_leapfrog_step_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _vp]),
     "u1_leapfrog_steps_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _i, C.POINTER(_i), _vp]),
     "u1_momenta_rows": (_i, [_vp, _u64, _u64, _u64, C.c_longlong, _i, _i, _i, _vp]),
+    "u1_momenta_rows_dev": (_i, [_vp, _u64, _u64, _u64, _vp, C.c_longlong, _i, _i, _i, _vp]),
     "u1_drift_wrap": (_i, [_vp, _vp, _vp, _d, _sz, _vp]),
     "u1_metropolis_sums": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "u1_metropolis_sums_dev": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "u1_select_accepted": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "u1_slab_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_create": (_i, [C.POINTER(_vp), _i, _vp, _sz]),

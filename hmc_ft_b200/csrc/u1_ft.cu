@@ -56,7 +56,7 @@ constexpr double kGeluZmax = 8.5, kGeluInvH = 8.0;
 constexpr int kGeluIntervals = 137, kGeluDeg = 9, kGeluStride = 11;
 constexpr double kGeluZmax = 8.5, kGeluInvH = 16.0;
 #endif
-constexpr int kGeluTableDoubles = kGeluIntervals * kGeluStride;
+constexpr int kGeluTableDoubles = (kGeluIntervals * kGeluStride + 1) & ~1;   // even: moved in 16-byte chunks
 
 #if U1_GELU_V == 1
 // Interval i is centred at i/8 (i = -68..68, row i+68 of the table); i = rint(8 z) comes for free from
@@ -249,6 +249,17 @@ constexpr int kTileStages = 3;
 #ifndef U1_TILE_FWD_ROWS
 #define U1_TILE_FWD_ROWS 2
 #endif
+// Measured on B200 (rnet3, 342 chains, one force; profiles/r01_ft_variants_epilogue.log): baseline 18.76 ms;
+// CCTL prefetch 20.49; row-batched operand loads 23.33; cp.async table 18.61 -> only the last one is on.
+#ifndef U1_EPI_PREFETCH      // L2 prefetch of the epilogue operands before the channel loop
+#define U1_EPI_PREFETCH 0
+#endif
+#ifndef U1_EPI_BATCH         // epilogue operands loaded one output row at a time
+#define U1_EPI_BATCH 0
+#endif
+#ifndef U1_TAB_CPASYNC       // GELU table staged by cp.async (joins the first tile's group)
+#define U1_TAB_CPASYNC 1
+#endif
 
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
 __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))
@@ -263,8 +274,15 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
     double* tile = s_dyn;                             // [kTileStages][TILE]
     double* s_tab = s_dyn + kTileStages * TILE;       // GELU table (forward epilogues only)
     asm volatile("griddepcontrol.launch_dependents;");
-    if (EPI != EPI_BWD) {
+    if (EPI != EPI_BWD) {                             // table rides in the first cp.async group (not needed before the epilogue)
+#if U1_TAB_CPASYNC
+        for (int i = 2 * threadIdx.x; i < kGeluTableDoubles; i += 2 * kConvThreads) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_tab + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gelu_tab + i));
+        }
+#else
         for (int i = threadIdx.x; i < kGeluTableDoubles; i += kConvThreads) s_tab[i] = gelu_tab[i];
+#endif
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     constexpr int groups_per_chain = V / ROWS;
@@ -296,6 +314,17 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
     for (int st = 0; st < kTileStages - 1; ++st) issue(st, st);
     const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
     const int r0 = ROWS * tp;
+    const size_t ob = (size_t)b * COUT * V + (size_t)x * LL + y;
+    if (U1_EPI_PREFETCH && (threadIdx.x & 15) == 0) { // one request per 128-byte line
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                const size_t idx = ob + (size_t)o * V + (size_t)r * LL;
+                if (add) asm volatile("prefetch.global.L2 [%0];" ::"l"(add + idx));
+                if (EPI == EPI_BWD && mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul + idx));
+            }
+    }
 #pragma unroll 1
     for (int c = 0; c < CIN; ++c) {
         if (c + kTileStages - 1 <= CIN) asm volatile("cp.async.wait_group %0;" ::"n"(kTileStages - 2));
@@ -322,26 +351,45 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
                     for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
                 }
     }
-    const size_t ob = (size_t)b * COUT * V + (size_t)x * LL + y;
+    // Epilogue operands (skip connection, GELU') were written several launches ago and come from DRAM:
+    // they were prefetched into L2 before the channel loop and are loaded one output row at a time
+    // (COUT independent loads in flight) instead of one exposed latency per value.
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r) {
+        const size_t rb = ob + (size_t)r * LL;
+        double ad[COUT], ml[COUT];
+#if U1_EPI_BATCH
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
-            const size_t idx = ob + (size_t)o * V + (size_t)r * LL;
+            ad[o] = add ? add[rb + (size_t)o * V] : 0.0;
+            ml[o] = (EPI == EPI_BWD && mul) ? mul[rb + (size_t)o * V] : 1.0;
+        }
+#endif
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const size_t idx = rb + (size_t)o * V;
             if (EPI == EPI_BWD) {
+#if !U1_EPI_BATCH
+                ad[o] = add ? add[idx] : 0.0;
+                ml[o] = (EPI == EPI_BWD && mul) ? mul[idx] : 1.0;
+#endif
                 double rv = acc[r][o];
-                if (add) rv += add[idx];
-                if (mul) rv *= mul[idx];
+                if (add) rv += ad[o];
+                if (mul) rv *= ml[o];
                 out[idx] = rv;
             } else {
+#if !U1_EPI_BATCH
+                ad[o] = add ? add[idx] : 0.0;
+#endif
                 double z = acc[r][o];
-                if (add) z += add[idx];
+                if (add) z += ad[o];
                 double g, d;
                 gelu_and_grad(s_tab, z, g, d);
                 out[idx] = g;
                 if (dout) dout[idx] = d;
             }
         }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -516,8 +564,8 @@ __global__ void k_ft_features(const double* __restrict__ th, double* __restrict_
     const bool mP = ss.mu == 0 ? ((x & 1) != ss.a) : ((y & 1) != ss.b);      // utils.py:52-80
     const bool mR = !active_site;                                             // utils.py:82-115
     double sP = 0.0, cP = 1.0, sR = 0.0, cR = 1.0;
-    if (mP) sincos(g.P(x, y), &sP, &cP);
-    if (mR) sincos(ss.mu == 0 ? g.R1(x, y) : g.R0(x, y), &sR, &cR);
+    if (mP) fast_sincos(g.P(x, y), sP, cP);
+    if (mR) fast_sincos(ss.mu == 0 ? g.R1(x, y) : g.R0(x, y), sR, cR);
     double* o = X + (size_t)b * kXC * V + r;
     o[0] = sP;
     o[(size_t)V] = cP;
@@ -555,7 +603,7 @@ k_ft_update(const double* __restrict__ th, const double* __restrict__ K, double*
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 double sn, cs;
-                sincos(t.A[q], &sn, &cs);
+                fast_sincos(t.A[q], sn, cs);
                 const double kq = Kb[(size_t)term_channel(ss.mu, q) * V];
                 d[q] = kq * (term_sign(ss.mu, q) * sn);
                 j[q] = kq * (-cs);
@@ -665,7 +713,7 @@ k_ft_update_bwd(const double* __restrict__ th, const double* __restrict__ K,
         double sn[6], cs[6], kq[6], jq[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-            sincos(t.A[q], &sn[q], &cs[q]);
+            fast_sincos(t.A[q], sn[q], cs[q]);
             kq[q] = Kb[(size_t)term_channel(ss.mu, q) * V];
             jq[q] = kq[q] * (-cs[q]);
         }
@@ -703,7 +751,7 @@ __global__ void k_ft_feat_bwd(const double* __restrict__ th, const double* __res
     const bool mP = ss.mu == 0 ? ((x & 1) != ss.a) : ((y & 1) != ss.b);
     if (mP) {
         double sn, cs;
-        sincos(g.P(x, y), &sn, &cs);
+        fast_sincos(g.P(x, y), sn, cs);
         pt += xb[r] * cs - xb[(size_t)V + r] * sn;
     }
     // rectangle adjoint of the CNN-feature type at location (xx,yy)
@@ -713,10 +761,10 @@ __global__ void k_ft_feat_bwd(const double* __restrict__ th, const double* __res
         const int q = xw * L + yw;
         double sn, cs;
         if (ss.mu == 0) {            // features use R1: channels 3 (sin), 5 (cos)
-            sincos(g.R1(xw, yw), &sn, &cs);
+            fast_sincos(g.R1(xw, yw), sn, cs);
             return xb[(size_t)3 * V + q] * cs - xb[(size_t)5 * V + q] * sn;
         } else {                     // features use R0: channels 2 (sin), 4 (cos)
-            sincos(g.R0(xw, yw), &sn, &cs);
+            fast_sincos(g.R0(xw, yw), sn, cs);
             return xb[(size_t)2 * V + q] * cs - xb[(size_t)4 * V + q] * sn;
         }
     };
@@ -788,9 +836,9 @@ __global__ void k_plain_force(const double* __restrict__ th, double* __restrict_
     const int b = s / V, r = s - b * V, x = r / L, y = r - x * L;
     const double* t0 = th + (size_t)b * 2 * V;
     Lat g{t0, t0 + V, L};
-    const double sp = sin(wrap_pi(g.P(x, y)));
-    F[(size_t)b * 2 * V + r] = beta * (sp - sin(wrap_pi(g.P(x, y - 1))));
-    F[(size_t)b * 2 * V + V + r] = beta * (-sp + sin(wrap_pi(g.P(x - 1, y))));
+    const double sp = fast_sin(g.P(x, y));                    // sin(wrap P) = sin P
+    F[(size_t)b * 2 * V + r] = beta * (sp - fast_sin(g.P(x, y - 1)));
+    F[(size_t)b * 2 * V + V + r] = beta * (-sp + fast_sin(g.P(x - 1, y)));
 }
 
 // H = -beta*sums[0] - logdet + 0.5*sums[2]  -> Hout[b]; also S_ft
@@ -884,18 +932,18 @@ static inline int ew_grid_ft(size_t n) {
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
-// Default chunk = the sites of EIGHT full waves of the widest kernel (k_conv 12->12 + GELU), i.e.
-// 444 chains at L=64: measured FT-force throughput grows with the chunk (15.5 TFLOP/s at one wave,
-// 20.1 at eight) because kernel-boundary ramps amortise; the convolutions are FP64-bound, so the
-// activations streaming through HBM (~290 B per site-layer) are hidden behind the math.
+// Default chunk: as many sites as fit a quarter of the device memory at the rnet3 workspace cost
+// (~7.4 KB per site: theta^(0..8), features, activations, K and GELU' of 8 subsets x 8 layers), i.e. all 1024
+// chains of C4 in one chunk (30 GB of the 180 GB) on a B200.  Measured FT-force throughput grows
+// monotonically with the chunk because kernel-boundary ramps and tails amortise (rnet3, L=64: 15.5 TFLOP/s at
+// 55 chains, 22.7 at 342, 23.1 at 512, 23.4 at 1024; an attempt to cut chunks at whole-wave sizes instead,
+// 370+370+284, was slower than three equal chunks); the convolutions are FP64-bound, so the activations
+// streaming through HBM (~290 B per site-layer) are hidden behind the math.
 static long long default_chunk_sites() {
-    int dev = 0, sms = 0, nb = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 227328;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 227328;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_conv<kW, kW, EPI_GELU>, kConvThreads,
-                                                      (size_t)kGeluTableDoubles * sizeof(double)) != cudaSuccess || nb < 1)
-        return 227328;
-    return (long long)sms * nb * kConvThreads * 2 * 8;     // 8 waves: launch/ramp overheads amortised
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || total_b == 0) return 1818624;
+    const long long sites = (long long)(total_b / 4 / 7400);
+    return sites < 227328 ? 227328 : sites;
 }
 static std::atomic<long long> g_chunk_sites{-1};
 static long long chunk_sites() {
@@ -922,6 +970,7 @@ static int lanes_for(int B) {
     }
     return B >= 2 ? max_lanes : 1;
 }
+static std::atomic<bool> g_chunk_explicit{false};
 static int chunk_chains(int B, int L) {
     const long long target = chunk_sites();
     long long c = target / ((long long)L * L);
@@ -1194,8 +1243,14 @@ static int ft_force_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double b
 extern "C" {
 
 long long u1ft_set_chunk_sites(long long sites) {
-    const long long prev = chunk_sites();
-    g_chunk_sites.store(sites < 1 ? 1 : sites);
+    const long long prev = g_chunk_explicit.load() ? chunk_sites() : 0;     // 0 = automatic (wave-aware) choice
+    if (sites < 1) {
+        g_chunk_sites.store(-1);
+        g_chunk_explicit.store(false);
+    } else {
+        g_chunk_sites.store(sites);
+        g_chunk_explicit.store(true);
+    }
     return prev;
 }
 

@@ -77,7 +77,8 @@ __global__ void k_momenta(double* __restrict__ pi, uint64_t seed, uint64_t chain
 }
 
 __global__ void k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t chain, uint64_t traj,
-                               long long x_first, int Lx, int L, int Lxg) {
+                               const uint64_t* __restrict__ traj_dev, long long x_first, int Lx, int L, int Lxg) {
+    if (traj_dev) traj += *traj_dev;                  // device-resident trajectory counter (CUDA-graph replay)
     const long long n = (long long)Lx * L;
     const PhiloxKey key = chain_key(seed, chain);
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
@@ -524,11 +525,12 @@ __global__ void k_obs_from_sums(const double* __restrict__ sums, double* __restr
 // Metropolis decision for the streaming path (hmc_u1.py:84-97).
 __global__ void k_metropolis(const double* __restrict__ s_old, const double* __restrict__ s_new,
                              const double* __restrict__ u_inject, uint64_t seed, uint64_t chain0,
-                             uint64_t traj, int B, double beta, double inv_vol,
+                             uint64_t traj, const uint64_t* __restrict__ traj_dev, int B, double beta, double inv_vol,
                              double* out_dH, int32_t* out_acc, double* out_H, double* out_plaq,
                              double* out_topo, int32_t* acc_flag) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (traj_dev) traj += *traj_dev;
     const double* o = s_old + (size_t)b * 3;
     const double* n = s_new + (size_t)b * 3;
     const double H_old = (-beta) * o[0] + 0.5 * o[2];
@@ -1036,14 +1038,18 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
     return U1_OK;
 }
 
-int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
-                    long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
+int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
+                        long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
     g_launches = 0;
     if (!pi || Lx <= 0 || L <= 0 || Lx_global <= 0) return U1_ERR_ARG;
-    k_momenta_rows<<<ew_grid((size_t)Lx * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, x_first, Lx, L, Lx_global);
+    k_momenta_rows<<<ew_grid((size_t)Lx * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, traj_dev, x_first, Lx, L, Lx_global);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
+}
+int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
+                    long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
+    return u1_momenta_rows_dev(pi, seed, chain, traj, nullptr, x_first, Lx, L, Lx_global, stream);
 }
 
 // n_steps fused steps ping-ponging between (thA,piA) and (thB,piB); returns where the result is.
@@ -1119,7 +1125,7 @@ int u1_trajectory(double* theta, const double* pi_inject, const double* u_inject
         U1_TRY(launch_sums(fin, nullptr, cp, w.s_new, w.partial, B, L, L, st));
         const size_t o = (size_t)t * B;
         k_metropolis<<<(B + 127) / 128, 128, 0, st>>>(
-            w.s_old, w.s_new, u_inject ? u_inject + o : nullptr, seed, chain0, traj, B, beta, inv_vol,
+            w.s_old, w.s_new, u_inject ? u_inject + o : nullptr, seed, chain0, traj, nullptr, B, beta, inv_vol,
             out_dH ? out_dH + o : nullptr, out_accept ? out_accept + o : nullptr,
             out_H ? out_H + o : nullptr, out_plaq ? out_plaq + o : nullptr,
             out_topo ? out_topo + o : nullptr, w.acc);
@@ -1161,18 +1167,25 @@ int u1_drift_wrap(const double* theta, const double* pi, double* out, double a, 
     return U1_OK;
 }
 
-int u1_metropolis_sums(const double* sums_old, const double* sums_new, const double* u_inject,
-                       uint64_t seed, uint64_t chain0, uint64_t traj, int B, double beta, double volume,
-                       double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
-                       double* out_topo, u1_stream_t stream) {
+int u1_metropolis_sums_dev(const double* sums_old, const double* sums_new, const double* u_inject,
+                           uint64_t seed, uint64_t chain0, uint64_t traj, const uint64_t* traj_dev, int B,
+                           double beta, double volume, double* out_dH, int32_t* out_accept, double* out_H,
+                           double* out_plaq, double* out_topo, u1_stream_t stream) {
     g_launches = 0;
     if (!sums_old || !sums_new || !out_accept || B <= 0 || !(volume > 0)) return U1_ERR_ARG;
     k_metropolis<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        sums_old, sums_new, u_inject, seed, chain0, traj, B, beta, 1.0 / volume, out_dH, nullptr, out_H,
+        sums_old, sums_new, u_inject, seed, chain0, traj, traj_dev, B, beta, 1.0 / volume, out_dH, nullptr, out_H,
         out_plaq, out_topo, out_accept);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
+}
+int u1_metropolis_sums(const double* sums_old, const double* sums_new, const double* u_inject,
+                       uint64_t seed, uint64_t chain0, uint64_t traj, int B, double beta, double volume,
+                       double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
+                       double* out_topo, u1_stream_t stream) {
+    return u1_metropolis_sums_dev(sums_old, sums_new, u_inject, seed, chain0, traj, nullptr, B, beta, volume,
+                                  out_dH, out_accept, out_H, out_plaq, out_topo, stream);
 }
 
 int u1_select_accepted(double* theta, const double* theta_new, const int32_t* accept,

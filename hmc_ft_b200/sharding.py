@@ -13,6 +13,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Dict, Optional, Tuple
 
@@ -120,6 +121,12 @@ class SlabHMC:
         # ext[f][mu][row][y], f = 0 theta, 1 pi ; two buffers for the out-of-place step kernel
         self._ext = [torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev) for _ in range(2)]
         self._sums = torch.zeros(3, dtype=torch.float64, device=self._dev)
+        # CUDA-graph replay of the trajectory: on by default for a single rank; with NCCL halo exchanges inside
+        # the capture (world > 1) it is opt-in (U1_SLAB_GRAPH=1) - a 2-GPU run with it hung in round 1.
+        self._graph_mode = os.environ.get("U1_SLAB_GRAPH", "1" if self.world == 1 else "0") == "1"
+        self._graph = None
+        self._eager_calls = 0
+        self.graph_error: Optional[str] = None
 
     def initialize(self) -> torch.Tensor:
         return torch.zeros(2, self.Lx, self.L, dtype=torch.float64, device=self._dev)
@@ -143,18 +150,70 @@ class SlabHMC:
 
     def trajectory(self, theta_own: torch.Tensor, u: Optional[float] = None) -> Dict[str, torch.Tensor]:
         """One Metropolis step.  theta_own [2,Lx,L] (this rank's rows, contiguous fp64 on the device) is
-        updated in place.  Returns 1-element device tensors dH, accept, H, plaq, topo (no host sync)."""
+        updated in place.  Returns 1-element device tensors dH, accept, H, plaq, topo (no host sync).
+
+        After two eager trajectories the whole step (about 60 kernel launches, the halo exchanges and the
+        two all-reduces) is captured once into a CUDA graph and replayed: the trajectory index lives in a
+        device counter that the graph increments (u1_momenta_rows_dev / u1_metropolis_sums_dev), so the
+        replay draws fresh momenta and a fresh accept uniform.  `U1_SLAB_GRAPH=0`, an injected `u`, or a
+        failed capture keep the eager path; with more than one rank the graph path is opt-in
+        (`U1_SLAB_GRAPH=1`): capturing the NCCL send/recv of the halo exchange is not validated."""
+        if self._graph_mode and u is None and theta_own.is_cuda:
+            key = (theta_own.data_ptr(), tuple(theta_own.shape))
+            g = self._graph
+            if g is not None and g["key"] == key:
+                return self._replay(g)
+            if self._eager_calls >= 2 or g is not None:
+                g = self._capture(theta_own, key)
+                if g is not None:
+                    return self._replay(g)
+        self._eager_calls += 1
+        return self._trajectory_body(theta_own, u, self.traj_counter, None)
+
+    def _replay(self, g) -> Dict[str, torch.Tensor]:
+        g["graph"].replay()
+        self.traj_counter += 1
+        self.gpu_launches += g["launches"]
+        self.halo.n_exchanges += g["exchanges"]
+        self.halo.bytes_sent += g["bytes"]
+        return {k: v.clone() for k, v in g["out"].items()}
+
+    def _capture(self, theta_own: torch.Tensor, key):
+        dev = self._dev
+        try:
+            with torch.cuda.device(dev):
+                ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # trajectories since capture
+                l0, e0, b0, t0 = self.gpu_launches, self.halo.n_exchanges, self.halo.bytes_sent, self.traj_counter
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self._trajectory_body(theta_own, None, t0, ctr)
+                    ctr += 1
+            g = {"key": key, "graph": graph, "out": out, "ctr": ctr, "launches": self.gpu_launches - l0,
+                 "exchanges": self.halo.n_exchanges - e0, "bytes": self.halo.bytes_sent - b0}
+            # capture executes nothing: undo the host-side bookkeeping of the captured pass
+            self.gpu_launches, self.halo.n_exchanges, self.halo.bytes_sent, self.traj_counter = l0, e0, b0, t0
+            self._graph = g
+            return g
+        except Exception as e:  # noqa: BLE001 - any capture failure falls back to the eager path for good
+            self._graph_mode = False
+            self._graph = None
+            self.graph_error = f"{type(e).__name__}: {e}"
+            return None
+
+    def _trajectory_body(self, theta_own: torch.Tensor, u: Optional[float], traj: int,
+                         ctr: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
         L, Lx, k, dt = self.L, self.Lx, self.k, self.dt
         lib, dev = self._lib, self._dev
-        traj = self.traj_counter
+        ctr_p = None if ctr is None else ctr.data_ptr()
         cur, nxt = self._ext
         own = slice(k, k + Lx)
         with torch.cuda.device(dev):
             sp = stream_ptr(dev)
             cur[0, :, own] = theta_own
             # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
-            self._call(lib.u1_momenta_rows(cur[1].data_ptr(), self.seed, self.chain, traj, self.x0 - k,
-                                           Lx + 2 * k, L, L, sp), "u1_momenta_rows")
+            self._call(lib.u1_momenta_rows_dev(cur[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
+                                               Lx + 2 * k, L, L, sp), "u1_momenta_rows")
             self.halo.exchange(cur[0])                      # theta halos
             th_c = cur[0, :, own].contiguous()
             pi_c = cur[1, :, own].contiguous()
@@ -187,12 +246,16 @@ class SlabHMC:
             out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
             out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
             u_d = None if u is None else torch.tensor([float(u)], dtype=torch.float64, device=dev)
-            self._call(lib.u1_metropolis_sums(s_old.data_ptr(), s_new.data_ptr(), None if u_d is None else u_d.data_ptr(),
-                                              self.seed, self.chain, traj, 1, self.beta, float(L) * L,
-                                              out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
-                                              out["plaq"].data_ptr(), out["topo"].data_ptr(), sp), "u1_metropolis_sums")
+            self._call(lib.u1_metropolis_sums_dev(s_old.data_ptr(), s_new.data_ptr(),
+                                                  None if u_d is None else u_d.data_ptr(),
+                                                  self.seed, self.chain, traj, ctr_p, 1, self.beta, float(L) * L,
+                                                  out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
+                                                  out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
+                       "u1_metropolis_sums")
             self._call(lib.u1_select_accepted(theta_own.data_ptr(), th_new.data_ptr(), out["accept"].data_ptr(),
                                               theta_own.numel(), 1, sp), "u1_select_accepted")
-        self._ext = [cur, nxt]
-        self.traj_counter += 1
+        if ctr is None:
+            # (under capture the buffer roles must stay as they were: every replay starts from them)
+            self._ext = [cur, nxt]
+            self.traj_counter += 1
         return out

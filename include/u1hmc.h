@@ -137,6 +137,11 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
  * on the decomposition. */
 int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
                     long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream);
+/* Same, with the trajectory index taken as traj + *traj_dev (traj_dev: device pointer to a uint64 counter,
+ * may be NULL): lets a captured CUDA graph of a slab trajectory be replayed with a counter that the graph
+ * itself increments, instead of a launch parameter frozen at capture time. */
+int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
+                        long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream);
 /* out = regularize(theta + a*pi), elementwise over n doubles (last half drift, hmc_u1.py:78-79). */
 int u1_drift_wrap(const double* theta, const double* pi, double* out, double a, size_t n,
                   u1_stream_t stream);
@@ -148,6 +153,11 @@ int u1_metropolis_sums(const double* sums_old, const double* sums_new, const dou
                        uint64_t seed, uint64_t chain0, uint64_t traj, int B, double beta, double volume,
                        double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq,
                        double* out_topo, u1_stream_t stream);
+/* Same, with the trajectory index taken as traj + *traj_dev (see u1_momenta_rows_dev). */
+int u1_metropolis_sums_dev(const double* sums_old, const double* sums_new, const double* u_inject,
+                           uint64_t seed, uint64_t chain0, uint64_t traj, const uint64_t* traj_dev, int B,
+                           double beta, double volume, double* out_dH, int32_t* out_accept, double* out_H,
+                           double* out_plaq, double* out_topo, u1_stream_t stream);
 /* theta[b] = theta_new[b] for every chain with accept[b] != 0 (per_chain doubles per chain). */
 int u1_select_accepted(double* theta, const double* theta_new, const int32_t* accept,
                        size_t per_chain, int B, u1_stream_t stream);
@@ -166,10 +176,12 @@ typedef struct u1ft_handle_s* u1ft_handle_t;
 int u1ft_create(u1ft_handle_t* out, int n_res_blocks, const double* weights, size_t n_doubles);
 int u1ft_destroy(u1ft_handle_t h);
 size_t u1ft_weight_count(int n_res_blocks);
-/* Tunable: lattice sites (chains x L^2) processed per kernel launch by the FT entry points, chosen
- * (default: eight full waves of the 12->12 conv kernel, 1818624 sites = 444 chains at L=64 on a
- * 148-SM B200; also settable through the environment variable U1FT_CHUNK_SITES).  Larger chunks
- * amortise kernel-boundary ramps; the workspace grows linearly with it.  Returns the previous value. */
+/* Tunable: lattice sites (chains x L^2) processed per kernel launch by the FT entry points.  By default
+ * (sites <= 0, or never called and no U1FT_CHUNK_SITES in the environment) the library uses as many sites
+ * as fit a quarter of the device memory at the rnet3 workspace cost (~7.4 KB per site; all 1024 chains of
+ * the L=64 benchmark in one 30 GB chunk on a 180 GB B200).  The chains are cut into equal chunks of at most
+ * that many sites.  Larger chunks amortise kernel-boundary ramps; the workspace grows linearly.  Returns
+ * the previous explicit value (0 = automatic), so passing the return value back restores the behaviour. */
 long long u1ft_set_chunk_sites(long long sites);
 /* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);
