@@ -55,8 +55,8 @@ __global__ void k_regularize(const double* __restrict__ in, double* __restrict__
 }
 
 // theta_out = regularize(theta + a*pi): last half drift of hmc_u1.py:78-79.
-__global__ void k_final_drift(const double* __restrict__ th, const double* __restrict__ pi,
-                              double* __restrict__ out, double a, size_t n) {
+__global__ void k_final_drift(const double* th, const double* __restrict__ pi,
+                              double* out, double a, size_t n) {      // out may alias th (in-place slab update)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x)
         out[i] = wrap_pi(fma(a, pi[i], th[i]));
@@ -453,23 +453,27 @@ constexpr int kSumRowsPerBlock = 16;
 
 __global__ void __launch_bounds__(kSumThreads)
 k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
-               const double* __restrict__ pi, double* __restrict__ partial, int Lx, int L, int nblk) {
+               const double* __restrict__ pi, double* __restrict__ partial, int Lx, int L, int nblk, int rpb,
+               size_t plane, int dn_in_place) {
+    // plane = distance between the mu=0 and mu=1 planes (Lx*L for a contiguous field; larger inside a slab's
+    // halo-extended buffer, where the row after the last own row IS the lower neighbour's first row).
     __shared__ double red[3 * 32];
-    const size_t V = (size_t)Lx * L;
+    const size_t V = plane;
     const double* t0 = th + (size_t)blockIdx.y * 2 * V;
     const double* t1 = t0 + V;
-    const int xa = blockIdx.x * kSumRowsPerBlock;
-    const int xb = min(Lx, xa + kSumRowsPerBlock);
+    const int xa = blockIdx.x * rpb;
+    const int xb = min(Lx, xa + rpb);
     double v[3] = {0.0, 0.0, 0.0};
     for (int i = threadIdx.x; i < (xb - xa) * L; i += kSumThreads) {
         const int x = xa + i / L, y = i % L;
         const int yp = wrapi(y + 1, L);
         double t1dn;
-        if (x + 1 < Lx) t1dn = t1[(size_t)(x + 1) * L + y];
+        if (x + 1 < Lx || dn_in_place) t1dn = t1[(size_t)(x + 1) * L + y];
         else t1dn = th_dn ? th_dn[L + y] : t1[y];
-        const double w = wrap_pi(t0[(size_t)x * L + y] - t1[(size_t)x * L + y] - t0[(size_t)x * L + yp] + t1dn);
-        v[0] += cos(w);
-        v[1] += w;
+        // cos(wrap P) = cos P; wrap_fast agrees with utils.py:182-187 to its rounding (u1_fastmath.cuh)
+        const double P = t0[(size_t)x * L + y] - t1[(size_t)x * L + y] - t0[(size_t)x * L + yp] + t1dn;
+        v[0] += fast_cos(P);
+        v[1] += wrap_fast(P);
         if (pi) {
             const double* q = pi + (size_t)blockIdx.y * 2 * V;
             const double a = q[(size_t)x * L + y], b = q[V + (size_t)x * L + y];
@@ -483,27 +487,39 @@ k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
     }
 }
 
-__global__ void k_finish_sums(const double* __restrict__ partial, double* __restrict__ sums, int B, int nblk) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (int k = 0; k < nblk; ++k) {
+// one CTA per chain: fixed-order (deterministic) reduction of the nblk partial triples
+__global__ void __launch_bounds__(128) k_finish_sums(const double* __restrict__ partial, double* __restrict__ sums, int nblk) {
+    __shared__ double red[3 * 32];
+    const int b = blockIdx.x;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int k = threadIdx.x; k < nblk; k += 128) {
         const double* p = partial + ((size_t)b * nblk + k) * 3;
-        s0 += p[0]; s1 += p[1]; s2 += p[2];
+        v[0] += p[0]; v[1] += p[1]; v[2] += p[2];
     }
-    sums[(size_t)b * 3 + 0] = s0; sums[(size_t)b * 3 + 1] = s1; sums[(size_t)b * 3 + 2] = s2;
+    block_sum<3>(v, red);
+    if (threadIdx.x == 0) {
+        sums[(size_t)b * 3 + 0] = v[0]; sums[(size_t)b * 3 + 1] = v[1]; sums[(size_t)b * 3 + 2] = v[2];
+    }
 }
 
-static inline int sum_blocks(int Lx) { return (Lx + kSumRowsPerBlock - 1) / kSumRowsPerBlock; }
+// Rows per CTA: 16 for big batches; fewer when B*Lx/16 CTAs would not fill the GPU (one lattice slab:
+// Lx=512 would be 32 CTAs), down to one row per CTA.
+static inline int sum_rows_per_block(int B, int Lx) {
+    int rpb = kSumRowsPerBlock;
+    while (rpb > 1 && (long long)B * ((Lx + rpb - 1) / rpb) < 148 * 8) rpb >>= 1;
+    return rpb;
+}
+static inline int sum_blocks(int B, int Lx) { const int r = sum_rows_per_block(B, Lx); return (Lx + r - 1) / r; }
 
 // sums: device [B][3]; partial: device [B][nblk][3]
 static int launch_sums(const double* th, const double* th_dn, const double* pi, double* sums,
-                       double* partial, int B, int Lx, int L, cudaStream_t st) {
-    const int nblk = sum_blocks(Lx);
-    k_partial_sums<<<dim3(nblk, B), kSumThreads, 0, st>>>(th, th_dn, pi, partial, Lx, L, nblk);
+                       double* partial, int B, int Lx, int L, cudaStream_t st, size_t plane = 0, int dn_in_place = 0) {
+    const int rpb = sum_rows_per_block(B, Lx), nblk = (Lx + rpb - 1) / rpb;
+    k_partial_sums<<<dim3(nblk, B), kSumThreads, 0, st>>>(th, th_dn, pi, partial, Lx, L, nblk, rpb,
+                                                          plane ? plane : (size_t)Lx * L, dn_in_place);
     count_launch();
     U1_CHECK_LAUNCH();
-    k_finish_sums<<<(B + 127) / 128, 128, 0, st>>>(partial, sums, B, nblk);
+    k_finish_sums<<<B, 128, 0, st>>>(partial, sums, nblk);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
@@ -844,7 +860,7 @@ struct PlainWs {
 static PlainWs carve_plain(void* ws, int B, int L) {
     PlainWs w;
     const size_t f = align_up((size_t)B * 2 * L * L * sizeof(double), 256);
-    const size_t part = align_up((size_t)B * sum_blocks(L) * 3 * sizeof(double), 256);
+    const size_t part = align_up((size_t)B * sum_blocks(B, L) * 3 * sizeof(double), 256);
     const size_t s3 = align_up((size_t)B * 3 * sizeof(double), 256);
     char* p = (char*)ws;
     w.thA = (double*)p; p += f;  w.piA = (double*)p; p += f;
@@ -1203,9 +1219,18 @@ int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, 
                  int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
     if (!theta || !theta_dn || !sums || Lx <= 0 || L <= 0) return U1_ERR_ARG;
-    const size_t need = (size_t)sum_blocks(Lx) * 3 * sizeof(double);
+    const size_t need = (size_t)sum_blocks(1, Lx) * 3 * sizeof(double);
     U1_TRY(check_ws(ws, ws_bytes, need));
     return launch_sums(theta, theta_dn, pi, sums, (double*)ws, 1, Lx, L, (cudaStream_t)stream);
+}
+
+int u1_slab_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* sums,
+                     int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_own || !sums || Lx <= 0 || L <= 0 || plane_stride < (size_t)(Lx + 1) * L) return U1_ERR_ARG;
+    const size_t need = (size_t)sum_blocks(1, Lx) * 3 * sizeof(double);
+    U1_TRY(check_ws(ws, ws_bytes, need));
+    return launch_sums(theta_own, nullptr, pi_own, sums, (double*)ws, 1, Lx, L, (cudaStream_t)stream, plane_stride, 1);
 }
 
 }  // extern "C"

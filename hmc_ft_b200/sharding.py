@@ -120,7 +120,7 @@ class SlabHMC:
         Lxe = self.Lx + 2 * self.k
         # ext[f][mu][row][y], f = 0 theta, 1 pi ; two buffers for the out-of-place step kernel
         self._ext = [torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev) for _ in range(2)]
-        self._sums = torch.zeros(3, dtype=torch.float64, device=self._dev)
+        self._sums6 = torch.zeros(6, dtype=torch.float64, device=self._dev)     # [old sums | new sums]
         # CUDA-graph replay of the trajectory: on by default for a single rank; with NCCL halo exchanges inside
         # the capture (world > 1) it is opt-in (U1_SLAB_GRAPH=1) - a 2-GPU run with it hung in round 1.
         self._graph_mode = os.environ.get("U1_SLAB_GRAPH", "1" if self.world == 1 else "0") == "1"
@@ -135,18 +135,6 @@ class SlabHMC:
     def _call(self, status, what):
         _lib.check(status, what)
         self.gpu_launches += _lib.last_launch_count()
-
-    def _global_sums(self, theta_own: torch.Tensor, theta_dn_row: torch.Tensor, pi_own: Optional[torch.Tensor]):
-        """[sum cos wrapP, sum wrapP, sum pi^2] over the whole lattice (all-reduced)."""
-        with torch.cuda.device(self._dev):
-            ws, nb = WS.get(self._dev, 4096 + 24 * (self.Lx // 16 + 2), "slab")
-            self._call(self._lib.u1_slab_sums(theta_own.data_ptr(), theta_dn_row.data_ptr(),
-                                              None if pi_own is None else pi_own.data_ptr(), self._sums.data_ptr(),
-                                              self.Lx, self.L, ws, nb, stream_ptr(self._dev)), "u1_slab_sums")
-        out = self._sums.clone()
-        if self.world > 1:
-            dist.all_reduce(out, group=self.group)
-        return out
 
     def trajectory(self, theta_own: torch.Tensor, u: Optional[float] = None) -> Dict[str, torch.Tensor]:
         """One Metropolis step.  theta_own [2,Lx,L] (this rank's rows, contiguous fp64 on the device) is
@@ -203,57 +191,63 @@ class SlabHMC:
 
     def _trajectory_body(self, theta_own: torch.Tensor, u: Optional[float], traj: int,
                          ctr: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """All device work of one trajectory, operating in place on the halo-extended buffers (no packing
+        copies apart from the halo send buffers): 1 copy-in, momenta, theta halo exchange, H_old sums, blocks
+        of <= k fused steps with a (theta,pi) exchange in between, final drift in place, theta halo exchange,
+        H_new sums, ONE all-reduce of the six sums, Metropolis, select."""
         L, Lx, k, dt = self.L, self.Lx, self.k, self.dt
         lib, dev = self._lib, self._dev
         ctr_p = None if ctr is None else ctr.data_ptr()
         cur, nxt = self._ext
         own = slice(k, k + Lx)
+        plane = (Lx + 2 * k) * L                             # doubles between the mu planes of an ext buffer
+        n_own = Lx * L
+        s6 = self._sums6
         with torch.cuda.device(dev):
             sp = stream_ptr(dev)
+            ws, nb = WS.get(dev, 4096 + 24 * (Lx + 2), "slab")     # up to one partial triple per row
             cur[0, :, own] = theta_own
             # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
             self._call(lib.u1_momenta_rows_dev(cur[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
                                                Lx + 2 * k, L, L, sp), "u1_momenta_rows")
             self.halo.exchange(cur[0])                      # theta halos
-            th_c = cur[0, :, own].contiguous()
-            pi_c = cur[1, :, own].contiguous()
-            dn_row = cur[0, :, k + Lx].contiguous()          # first row of the lower neighbour, [2][L]
-            s_old = self._global_sums(th_c, dn_row, pi_c)
+            self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
+                                            s6[0:3].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
             done = 0
             while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
                 if done > 0:
                     self.halo.exchange(cur)                  # theta and pi, k rows each side
-                nb = min(k, self.n_steps - done)
+                nblk = min(k, self.n_steps - done)
                 in_b = C.c_int(0)
                 self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
                                                       nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
-                                                      0.5 * dt if done == 0 else dt, dt, nb, C.byref(in_b), sp),
+                                                      0.5 * dt if done == 0 else dt, dt, nblk, C.byref(in_b), sp),
                            "u1_leapfrog_steps_rect")
                 if in_b.value:
                     cur, nxt = nxt, cur
-                done += nb
-            # final half drift + wrap on own rows (hmc_u1.py:78-79), then H_new
-            th_new = torch.empty(2, Lx, L, dtype=torch.float64, device=dev)
-            pi_c = cur[1, :, own].contiguous()
-            th_c = cur[0, :, own].contiguous()
-            self._call(lib.u1_drift_wrap(th_c.data_ptr(), pi_c.data_ptr(), th_new.data_ptr(), 0.5 * dt,
-                                         th_new.numel(), sp), "u1_drift_wrap")
-            cur[0, :, own] = th_new
+                done += nblk
+            # final half drift + wrap on own rows, in place (hmc_u1.py:78-79), then H_new
+            for mu in range(2):
+                t = cur[0, mu, k].data_ptr()
+                self._call(lib.u1_drift_wrap(t, cur[1, mu, k].data_ptr(), t, 0.5 * dt, n_own, sp), "u1_drift_wrap")
             self.halo.exchange(cur[0])
-            dn_row = cur[0, :, k + Lx].contiguous()
-            s_new = self._global_sums(th_new, dn_row, pi_c)
+            self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
+                                            s6[3:6].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
+            if self.world > 1:
+                dist.all_reduce(s6, group=self.group)
             # every rank takes the same decision from the all-reduced sums and the shared Philox draw
             out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
             out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
             u_d = None if u is None else torch.tensor([float(u)], dtype=torch.float64, device=dev)
-            self._call(lib.u1_metropolis_sums_dev(s_old.data_ptr(), s_new.data_ptr(),
+            self._call(lib.u1_metropolis_sums_dev(s6[0:3].data_ptr(), s6[3:6].data_ptr(),
                                                   None if u_d is None else u_d.data_ptr(),
                                                   self.seed, self.chain, traj, ctr_p, 1, self.beta, float(L) * L,
                                                   out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
                                                   out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
                        "u1_metropolis_sums")
-            self._call(lib.u1_select_accepted(theta_own.data_ptr(), th_new.data_ptr(), out["accept"].data_ptr(),
-                                              theta_own.numel(), 1, sp), "u1_select_accepted")
+            for mu in range(2):
+                self._call(lib.u1_select_accepted(theta_own[mu].data_ptr(), cur[0, mu, k].data_ptr(),
+                                                  out["accept"].data_ptr(), n_own, 1, sp), "u1_select_accepted")
         if ctr is None:
             # (under capture the buffer roles must stay as they were: every replay starts from them)
             self._ext = [cur, nxt]

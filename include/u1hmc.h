@@ -165,6 +165,12 @@ int u1_select_accepted(double* theta, const double* theta_new, const int32_t* ac
  * (pi may be NULL).  theta_dn as above (first row of the lower neighbour). */
 int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, double* sums,
                  int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* Same sums taken directly from a halo-extended slab buffer (no packing copies): theta_own / pi_own point
+ * at the first OWN row of the mu=0 plane, the mu=1 plane lies plane_stride doubles further, and the row
+ * after the last own row (the lower neighbour's first row, already exchanged) is read in place.
+ * plane_stride >= (Lx+1)*L.  pi_own may be NULL. */
+int u1_slab_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* sums,
+                     int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
 
 /* ---------------- FieldTransformation / HMC_U1_FT ---------------- */
 typedef struct u1ft_handle_s* u1ft_handle_t;

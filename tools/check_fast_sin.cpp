@@ -3,6 +3,7 @@
 //   winding vs that expression's floor, neg2_log vs logl (uniform, near 0, near 1).
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <random>
 #include "../hmc_ft_b200/csrc/u1_fastmath.cuh"
 static const u1::LogTabEntry kTab[u1::kLogTabN] = {
@@ -13,14 +14,15 @@ static double wrap_ref(double t) {                    // utils.py:182-187
     double w = (t - pi) / (2 * pi);
     return 2 * pi * (w - floor(w) - 0.5);
 }
-int main() {
+int main(int argc, char** argv) {
+    const long N = argc > 1 ? atol(argv[1]) : 10000000;      // samples per range
     std::mt19937_64 g(1);
     double worst = 0, wx = 0, worst_lib = 0, worst_c = 0, worst_sc = 0, worst_w = 0;
     long wind_bad = 0;
     for (double range : {3.2, 13.0, 40.0, 1000.0}) {
         std::uniform_real_distribution<double> d(-range, range);
         double w = 0, wc = 0;
-        for (long i = 0; i < 10000000; ++i) {
+        for (long i = 0; i < N; ++i) {
             double x = d(g);
             long double ref = sinl((long double)x), refc = cosl((long double)x);
             double e = fabs((double)((long double)u1::fast_sin(x) - ref));
@@ -64,11 +66,11 @@ int main() {
         if (ea > worst_abs) worst_abs = ea;
     };
     std::uniform_real_distribution<double> d01(0.0, 1.0);
-    for (long i = 0; i < 20000000; ++i) {
+    for (long i = 0; i < 2 * N; ++i) {
         const uint64_t m = g() >> 11;
         chk(((double)m + 0.5) * (1.0 / 9007199254740992.0));
     }
-    for (long i = 0; i < 2000000; ++i) {
+    for (long i = 0; i < N / 5; ++i) {
         chk(fmin(1.0, ldexp(d01(g) + 1e-3, -(int)(g() % 54))));   // small u (domain is (0,1])
         chk(1.0 - ldexp(d01(g) + 1e-3, -(int)(g() % 50) - 1));  // u -> 1
         chk(0.70710678118654752 + 1e-6 * (d01(g) - 0.5));       // around the mantissa split
