@@ -42,6 +42,8 @@ SIGNATURES = {
     "u1_select_accepted": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "u1_slab_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1_slab_sums_ext": (_i, [_vp, _vp, C.c_size_t, _vp, _i, _i, _vp, C.c_size_t, _vp]),
+    "u1_diff_power_sums_workspace_bytes": (C.c_size_t, []),
+    "u1_diff_power_sums": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp]),
     "u1ft_create": (_i, [C.POINTER(_vp), _i, _vp, _sz]),
     "u1ft_destroy": (_i, [_vp]),
     "u1ft_weight_count": (_sz, [_i]),

@@ -764,6 +764,32 @@ k_traj_resident(TrajArgs a) {
     }
 }
 
+// ---- training-loss reduction (field_trans_opt.py:452-458): sum |a-b|^p for p = 2,4,6,8 over n elements ----
+__global__ void __launch_bounds__(256) k_diff_pow_sums(const double* __restrict__ a, const double* __restrict__ b, size_t n,
+                                                       double* __restrict__ partial) {
+    __shared__ double red[4 * 32];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = a[i] - b[i], d2 = d * d, d4 = d2 * d2;
+        v[0] += d2; v[1] += d4; v[2] += d4 * d2; v[3] += d4 * d4;
+    }
+    block_sum<4>(v, red);
+    if (threadIdx.x == 0) {
+        double* o = partial + (size_t)blockIdx.x * 4;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+    }
+}
+__global__ void __launch_bounds__(128) k_finish_pow_sums(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+    __shared__ double red[4 * 32];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = threadIdx.x; k < nblk; k += 128) {
+        const double* p = partial + (size_t)k * 4;
+        v[0] += p[0]; v[1] += p[1]; v[2] += p[2]; v[3] += p[3];
+    }
+    block_sum<4>(v, red);
+    if (threadIdx.x == 0) { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; out[3] = v[3]; }
+}
+
 __global__ void __launch_bounds__(256) k_fp64_probe(double* __restrict__ out, int iters) {
     double a[8];
 #pragma unroll
@@ -927,6 +953,23 @@ int u1_autocorr(const double* topo, int T, int B, int max_lag, double two_v_chi,
     count_launch();
     U1_CHECK_LAUNCH();
     k_autocorr<<<dim3(max_lag + 1, B), 256, 0, st>>>(topo, T, B, two_v_chi, (const double*)ws, gamma_chi, gamma_def);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+size_t u1_diff_power_sums_workspace_bytes(void) { return (size_t)148 * 16 * 4 * sizeof(double); }
+
+int u1_diff_power_sums(const double* a, const double* b, size_t n, double* out4, void* ws, size_t ws_bytes,
+                       u1_stream_t stream) {
+    g_launches = 0;
+    if (!a || !b || !out4 || n == 0) return U1_ERR_ARG;
+    if (!ws || ws_bytes < u1_diff_power_sums_workspace_bytes() || (reinterpret_cast<uintptr_t>(ws) & 255u)) return U1_ERR_WORKSPACE;
+    const int nblk = ew_grid(n);
+    k_diff_pow_sums<<<nblk, 256, 0, (cudaStream_t)stream>>>(a, b, n, (double*)ws);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_finish_pow_sums<<<1, 128, 0, (cudaStream_t)stream>>>((const double*)ws, nblk, out4);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;

@@ -1,5 +1,7 @@
-"""FieldTransformation, inference half (2d_u1_cluster/field_trans_opt.py:26-398,654-692), on the
-sm_100a library.  Training (inverse / loss_fn / train*) is out of scope."""
+"""FieldTransformation (2d_u1_cluster/field_trans_opt.py:26-505,654-692) on the sm_100a library: forward,
+log-det, inverse, S_FT and its force, and the VALUE of the training loss (loss_fn / evaluate_step).
+Training itself (gradient of the loss with respect to the CNN weights, train_step / train) is out of scope
+(SURVEY §8f.4)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -266,3 +268,51 @@ class FieldTransformation:
                                             ws, nb, stream_ptr(self._dev)), "u1ft_force")
         self._count()
         return self._back(out, theta, single)
+
+    # ------------------------------------------------------------------ training loss, forward value
+    def compute_force(self, theta, beta, transformed: bool = False):
+        """field_trans_opt.py:400-441: force of -beta sum cos P (plain, u1_force) or of S_FT (u1ft_force).
+        Values only: the reference's create_graph=True (needed to differentiate the loss with respect to the
+        CNN weights) is the training path and stays out of scope."""
+        if transformed:
+            return self.new_force(theta, beta)
+        d, single, B = self._stage(theta)
+        out = torch.empty_like(d)
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.u1_force(d.data_ptr(), out.data_ptr(), B, self.L, float(beta), stream_ptr(self._dev)),
+                       "u1_force")
+        self._count()
+        return self._back(out, theta, single)
+
+    def loss_fn(self, theta_ori, train_beta: Optional[float] = None):
+        """field_trans_opt.py:443-462, forward value: theta_new = inverse(theta_ori); d = F_FT(theta_new;
+        train_beta) - F_plain(theta_new; 1); loss = sum_{p=2,4,6,8} ||d||_p / vol^(1/p) with the norms over the
+        whole batch tensor and vol = L^2.  Returns a 0-dim fp64 tensor on the device (no host sync)."""
+        beta = self.train_beta if train_beta is None else train_beta
+        if beta is None:
+            raise ValueError("loss_fn needs train_beta (set .train_beta or pass train_beta=)")
+        th_new = self.inverse(theta_ori)
+        d_new, _, B = self._stage(th_new)
+        f_ori = self.compute_force(d_new, 1.0)
+        f_new = self.compute_force(d_new, float(beta), transformed=True)
+        sums = torch.empty(4, dtype=torch.float64, device=self._dev)
+        with torch.cuda.device(self._dev):
+            ws, nb = WS.get(self._dev, self._lib.u1_diff_power_sums_workspace_bytes(), "loss")
+            _lib.check(self._lib.u1_diff_power_sums(f_new.data_ptr(), f_ori.data_ptr(), f_new.numel(), sums.data_ptr(),
+                                                    ws, nb, stream_ptr(self._dev)), "u1_diff_power_sums")
+        self._count()
+        p = torch.tensor([2.0, 4.0, 6.0, 8.0], dtype=torch.float64, device=self._dev)
+        vol = float(self.L * self.L)
+        return (sums.pow(1.0 / p) / vol ** (1.0 / p)).sum()
+
+    def evaluate_step(self, theta_ori) -> float:
+        """field_trans_opt.py:490-505: loss of one evaluation batch as a Python float."""
+        return float(self.loss_fn(theta_ori).item())
+
+    def train_step(self, theta_ori):
+        raise NotImplementedError("CNN training (double backward through the FT force) is outside the sampling hot path; "
+                                  "train with the reference and load the checkpoint (load_checkpoint / _load_best_model)")
+
+    def train(self, *args, **kwargs):
+        return self.train_step(None)
+

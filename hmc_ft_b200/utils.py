@@ -171,3 +171,29 @@ def auto_from_chi(topo, max_lag: int, beta: float, volume: int):
 def auto_by_def(topo, max_lag: int):
     """utils.py:264-298: normalised autocovariance; [T] or [T,B] histories."""
     return _autocorr(topo, max_lag, 1.0, "def")
+
+
+def auto_from_chi_bootstrap(topo, max_lag: int, beta: float, volume: int, n_bootstrap: int = 1000, random_seed=None):
+    """utils.py:300-365: bootstrap mean and standard deviation of auto_from_chi.  The resampling indices come
+    from numpy's legacy generator exactly as in the reference (np.random.seed(random_seed), one
+    np.random.choice(n, n) per bootstrap sample), so a seeded call reproduces the reference's numbers; the
+    n_bootstrap resampled histories are gathered on the device and all their autocorrelation functions are
+    evaluated by ONE u1_autocorr launch (one CTA per (lag, sample)) instead of n_bootstrap x max_lag numpy
+    passes.  Returns (mean[max_lag+1], std[max_lag+1]) as numpy arrays (ddof=0, as np.std)."""
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    as_t = torch.is_tensor(topo)
+    series = torch.round(topo.detach().to(torch.float64)) if as_t else torch.as_tensor(np.round(np.asarray(topo, dtype=np.float64)))
+    if series.dim() != 1:
+        raise ValueError("auto_from_chi_bootstrap expects one history [T]")
+    n = series.shape[0]
+    if max_lag >= n:
+        raise ValueError("max_lag must be smaller than the history length")
+    idx = np.stack([np.random.choice(n, size=n, replace=True) for _ in range(n_bootstrap)], axis=1)      # [T, n_bootstrap]
+    dev = require_cuda(series.device if series.is_cuda else None)
+    d = to_dev(series, dev)
+    resampled = d[torch.as_tensor(idx, device=dev)].contiguous()                                          # [T, n_bootstrap]
+    g = _autocorr(resampled, max_lag, 2 * volume * chi_infinity(beta), "chi")                             # [max_lag+1, n_bootstrap]
+    mean = g.mean(dim=1)
+    std = g.var(dim=1, unbiased=False).sqrt()
+    return mean.cpu().numpy(), std.cpu().numpy()

@@ -172,6 +172,13 @@ int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, 
 int u1_slab_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* sums,
                      int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
 
+/* Training-loss reduction (field_trans_opt.py:452-458): out4[k] = sum_i |a[i]-b[i]|^(2k+2), k = 0..3, over n
+ * doubles (deterministic two-phase reduction; out4 is device memory).  The loss is
+ * sum_k out4[k]^(1/p_k) / vol^(1/p_k), p_k = 2,4,6,8, formed by the caller. */
+size_t u1_diff_power_sums_workspace_bytes(void);
+int u1_diff_power_sums(const double* a, const double* b, size_t n, double* out4, void* ws, size_t ws_bytes,
+                       u1_stream_t stream);
+
 /* ---------------- FieldTransformation / HMC_U1_FT ---------------- */
 typedef struct u1ft_handle_s* u1ft_handle_t;
 /* field_trans_opt.py:654-692 (_load_best_model) + cnn_model_opt.py:6-247.

@@ -334,6 +334,22 @@ class FieldTransformationOracle:
         s = self.new_action(t, beta).sum()
         return torch.autograd.grad(s, t)[0].detach()
 
+    # ---- training loss, forward value only (field_trans_opt.py:400-460, 490-505) ----
+    def compute_force(self, theta, beta, transformed: bool = False):
+        """field_trans_opt.py:400-441: force of -beta sum cos P (no regularize) or of S_FT."""
+        if transformed:
+            return self.new_force(theta, beta)
+        return force_analytic(theta, beta)
+
+    def loss_fn(self, theta_ori, train_beta: float):
+        """field_trans_opt.py:443-462: theta_new = inverse(theta_ori); the four p-norms (p = 2,4,6,8, taken over
+        the WHOLE batch tensor) of F_FT(theta_new; train_beta) - F_plain(theta_new; beta=1), each divided by
+        vol^(1/p), vol = L^2."""
+        th_new, _ = self.inverse(theta_ori)
+        d = self.compute_force(th_new, train_beta, transformed=True) - self.compute_force(th_new, 1.0)
+        vol = float(self.L * self.L)
+        return sum(torch.norm(d, p=p) / vol ** (1.0 / p) for p in (2, 4, 6, 8))
+
 
 # --------------------------------------------------------------------------
 # Index-loop spec of one subset update (small L only; independent of torch.roll)
@@ -504,3 +520,19 @@ def auto_by_def(topo, max_lag: int) -> np.ndarray:
     for d in range(max_lag + 1):
         out[d] = 1.0 if d == 0 else np.mean((topo[:-d] - mean) * (topo[d:] - mean)) / var
     return out
+
+
+def auto_from_chi_bootstrap(topo, max_lag: int, beta: float, volume: int, n_bootstrap: int = 1000, random_seed=None):
+    """utils.py:300-365: bootstrap mean / std of auto_from_chi with numpy's legacy generator."""
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    topo = np.round(np.asarray(topo)).astype(int)
+    n = len(topo)
+    chi = chi_infinity(beta)
+    res = np.zeros((n_bootstrap, max_lag + 1))
+    for i in range(n_bootstrap):
+        bt = topo[np.random.choice(n, size=n, replace=True)]
+        res[i, 0] = 1.0
+        for d in range(1, max_lag + 1):
+            res[i, d] = 1 - np.mean((bt[:-d] - bt[d:]) ** 2) / (2 * volume * chi)
+    return np.mean(res, axis=0), np.std(res, axis=0)

@@ -279,3 +279,23 @@ def test_inverse_and_coefficients(golden_dir, tag, wfile):
     assert rel(K1.cpu().numpy()[m], z["K1_6"][m]) < 1e-12
     m0 = np.zeros_like(z["K0_6"], dtype=bool); m0[:, 2:4, 1::2, 0::2] = True
     assert rel(K0.cpu().numpy()[m0], z["K0_6"][m0]) < 1e-12 and float(K0[:, :2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tag,wfile", [("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L16", "weights_simple_beta6.0.npz")])
+def test_training_loss_value(golden_dir, tag, wfile):
+    """loss_fn / evaluate_step / compute_force (field_trans_opt.py:400-505), forward values, against the real
+    reference's numbers (tools/gen_golden_loss.py) and the oracle."""
+    z = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    L, beta = int(z["L"]), float(z["train_beta"])
+    ft = make_ft(golden_dir, L, wfile)
+    th_new = torch.tensor(z["theta_new"], device="cuda")
+    assert rel(ft.compute_force(th_new, 1.0), z["force_ori"]) < 1e-12
+    assert rel(ft.compute_force(th_new, beta, transformed=True), z["force_new"]) < 1e-12
+    ft.train_beta = beta
+    loss = ft.evaluate_step(torch.tensor(z["theta_ori"], device="cuda"))
+    assert abs(loss - float(z["loss"])) < 1e-9 * abs(float(z["loss"]))
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    want = O.FieldTransformationOracle(L, nets).loss_fn(torch.tensor(z["theta_ori"]), beta).item()
+    assert abs(ft.loss_fn(torch.tensor(z["theta_ori"]), train_beta=beta).item() - want) < 1e-9 * abs(want)
+    with pytest.raises(NotImplementedError):
+        ft.train_step(torch.tensor(z["theta_ori"]))

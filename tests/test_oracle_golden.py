@@ -140,6 +140,10 @@ def test_autocorrelation_matches_reference(golden_dir):
         a = O.auto_from_chi(z["topo"][:, b], int(z["max_lag"]), float(z["beta"]), int(z["volume"]))
         d = O.auto_by_def(z["topo"][:, b], int(z["max_lag"]))
         assert np.array_equal(a, z["auto_from_chi"][:, b]) and np.array_equal(d, z["auto_by_def"][:, b])
+    # utils.py:300-365 bootstrap, seeded legacy numpy generator
+    m, sd = O.auto_from_chi_bootstrap(z["topo"][:, 0], int(z["max_lag"]), float(z["beta"]), int(z["volume"]),
+                                      n_bootstrap=int(z["boot_n"]), random_seed=int(z["boot_seed"]))
+    assert np.array_equal(m, z["boot_mean"]) and np.array_equal(sd, z["boot_std"])
 
 
 @pytest.mark.parametrize("tag,wfile", [("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L16", "weights_simple_beta6.0.npz")])
@@ -151,3 +155,16 @@ def test_inverse_matches_reference(golden_dir, tag, wfile):
     back, iters = ft.inverse(T(z["theta_ori"]))
     assert rel(back, z["inverse"]) < 1e-13 and max(iters) < 200
     assert rel(back, z["theta_new"]) < 1e-4                      # debug/check_ft.py:113-118 threshold
+
+
+@pytest.mark.parametrize("tag,wfile", [("rnet3_L8", "weights_rnet3_beta6.0.npz"), ("simple_L16", "weights_simple_beta6.0.npz")])
+def test_training_loss_value_matches_reference(golden_dir, tag, wfile):
+    """field_trans_opt.py:400-505 loss_fn / evaluate_step (forward value) against the reference's numbers."""
+    z = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
+    ft = O.FieldTransformationOracle(int(z["L"]), nets)
+    th_new = T(z["theta_new"])
+    assert rel(ft.compute_force(th_new, 1.0), z["force_ori"]) < 1e-13
+    assert rel(ft.compute_force(th_new, float(z["train_beta"]), transformed=True), z["force_new"]) < 1e-12
+    loss = ft.loss_fn(T(z["theta_ori"]), float(z["train_beta"]))
+    assert abs(loss.item() - float(z["loss"])) < 1e-11 * abs(float(z["loss"]))

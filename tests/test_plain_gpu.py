@@ -259,6 +259,9 @@ def test_autocorrelation_device(hb, golden_dir):
     assert rel(d, z["auto_by_def"]) < 1e-12 and torch.all(d[:, 3] == 1.0)        # frozen chain -> all ones
     one = U.auto_from_chi(topo[:, 0], ml, beta, vol)                              # numpy in -> numpy out
     assert isinstance(one, np.ndarray) and one.shape == (ml + 1,) and rel(one, z["auto_from_chi"][:, 0]) < 1e-14
+    # bootstrap (utils.py:300-365): same seeded resampling, all samples in one launch
+    m, sd = U.auto_from_chi_bootstrap(topo[:, 0], ml, beta, vol, n_bootstrap=int(z["boot_n"]), random_seed=int(z["boot_seed"]))
+    assert m.shape == (ml + 1,) and rel(m, z["boot_mean"]) < 1e-12 and rel(sd, z["boot_std"]) < 1e-10
 
 
 def test_multistep_kernel_bit_identical_to_single_steps(hb):
