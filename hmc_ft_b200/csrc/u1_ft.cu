@@ -257,6 +257,9 @@ constexpr int kTileStages = 3;
 #ifndef U1_EPI_BATCH         // epilogue operands loaded one output row at a time
 #define U1_EPI_BATCH 0
 #endif
+#ifndef U1_ADD_AT_START      // skip operand folded into the accumulator start values: 1 forward layers, 2 reverse layers too
+#define U1_ADD_AT_START 2
+#endif
 #ifndef U1_TAB_CPASYNC       // GELU table staged by cp.async (joins the first tile's group)
 #define U1_TAB_CPASYNC 1
 #endif
@@ -305,16 +308,22 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
         }
         asm volatile("cp.async.commit_group;");
     };
-    double acc[ROWS][COUT];                           // forward layers start from the bias (one DADD less per value)
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[r][o] = (EPI == EPI_BWD) ? 0.0 : p.b[o];
 #pragma unroll
     for (int st = 0; st < kTileStages - 1; ++st) issue(st, st);
     const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
     const int r0 = ROWS * tp;
     const size_t ob = (size_t)b * COUT * V + (size_t)x * LL + y;
+    // Forward layers start from bias (+ skip connection): the skip operand comes from DRAM, and loading it
+    // here puts its latency under the wait for the first tile instead of exposing it once per value in
+    // the epilogue (U1_ADD_AT_START=0: old placement).
+    double acc[ROWS][COUT];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            acc[r][o] = (EPI == EPI_BWD) ? 0.0 : p.b[o];
+            if (U1_ADD_AT_START && (EPI != EPI_BWD || U1_ADD_AT_START > 1) && add) acc[r][o] += add[ob + (size_t)o * V + (size_t)r * LL];
+        }
     if (U1_EPI_PREFETCH && (threadIdx.x & 15) == 0) { // one request per 128-byte line
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
@@ -361,7 +370,7 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
 #if U1_EPI_BATCH
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
-            ad[o] = add ? add[rb + (size_t)o * V] : 0.0;
+            ad[o] = (add && !(U1_ADD_AT_START && (EPI != EPI_BWD || U1_ADD_AT_START > 1))) ? add[rb + (size_t)o * V] : 0.0;
             ml[o] = (EPI == EPI_BWD && mul) ? mul[rb + (size_t)o * V] : 1.0;
         }
 #endif
@@ -370,19 +379,19 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
             const size_t idx = rb + (size_t)o * V;
             if (EPI == EPI_BWD) {
 #if !U1_EPI_BATCH
-                ad[o] = add ? add[idx] : 0.0;
+                ad[o] = (add && U1_ADD_AT_START < 2) ? add[idx] : 0.0;
                 ml[o] = (EPI == EPI_BWD && mul) ? mul[idx] : 1.0;
 #endif
                 double rv = acc[r][o];
-                if (add) rv += ad[o];
+                if (add && U1_ADD_AT_START < 2) rv += ad[o];
                 if (mul) rv *= ml[o];
                 out[idx] = rv;
             } else {
 #if !U1_EPI_BATCH
-                ad[o] = add ? add[idx] : 0.0;
+                ad[o] = (add && !U1_ADD_AT_START) ? add[idx] : 0.0;
 #endif
                 double z = acc[r][o];
-                if (add) z += ad[o];
+                if (add && !U1_ADD_AT_START) z += ad[o];
                 double g, d;
                 gelu_and_grad(s_tab, z, g, d);
                 out[idx] = g;

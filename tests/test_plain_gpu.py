@@ -264,13 +264,16 @@ def test_autocorrelation_device(hb, golden_dir):
     assert m.shape == (ml + 1,) and rel(m, z["boot_mean"]) < 1e-12 and rel(sd, z["boot_std"]) < 1e-10
 
 
-def test_multistep_kernel_bit_identical_to_single_steps(hb):
+@pytest.mark.parametrize("Lx,L,B", [(72, 100, 2), (264, 1000, 3)])
+def test_multistep_kernel_bit_identical_to_single_steps(hb, Lx, L, B):
     """u1_leapfrog_steps_rect (temporally blocked, groups of 4 steps) == repeated u1_leapfrog_step,
-    bit for bit, on a rectangular periodic lattice whose sides are not multiples of the 56-site block."""
+    bit for bit, on rectangular periodic lattices whose sides are not multiples of the inner block; the
+    second case has more windows (630) than resident CTAs, so the persistent prefetching kernel walks
+    several windows per CTA."""
     import ctypes as C
     from hmc_ft_b200 import _lib
     lib = _lib.load()
-    Lx, L, B, n, beta, dt = 72, 100, 2, 7, 3.0, 0.07
+    n, beta, dt = 7, 3.0, 0.07
     g = torch.Generator().manual_seed(77)
     th = ((torch.rand(B, 2, Lx, L, generator=g, dtype=torch.float64) * 2 - 1) * 3).cuda()
     pi = torch.randn(B, 2, Lx, L, generator=g, dtype=torch.float64).cuda()
