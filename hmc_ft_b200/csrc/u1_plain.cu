@@ -277,7 +277,7 @@ __global__ void __launch_bounds__((kMsE / 2) * (EW / 4), 512 / ((kMsE / 2) * (EW
 k_leapfrog_multi(MultiArgs a) {
     constexpr int L = kMsE, TX = 2, TY = 4, NTX = L / TX, NTY = EW / TY, OW = EW - 2 * kMsHalo;
     // edge arrays are [i or j][tx][ty]: the 16 lanes of a half-warp (2 tx x 8 ty at EW=32) hit 16 distinct banks
-    extern __shared__ double dsm[];
+    extern __shared__ __align__(16) double dsm[];
     double* colA = dsm;
     double* rowA = colA + L * NTY;
     double* colB = rowA + NTX * TY * NTY;
@@ -320,18 +320,20 @@ k_leapfrog_multi(MultiArgs a) {
                 th0[i][j] = fma(dr, p0[i][j], th0[i][j]);
                 th1[i][j] = fma(dr, p1[i][j], th1[i][j]);
             }
-#pragma unroll
-        for (int i = 0; i < TX; ++i) colA[(i * NTX + tx) * NTY + ty] = th0[i][0];
-#pragma unroll
-        for (int j = 0; j < TY; ++j) rowA[(j * NTX + tx) * NTY + ty] = th1[0][j];
+        // edges as double2: column pair at [tx][ty], row quadruple as two double2 at [jp][tx][ty] (lanes 16 B apart)
+        reinterpret_cast<double2*>(colA)[tx * NTY + ty] = make_double2(th0[0][0], th0[1][0]);
+        reinterpret_cast<double2*>(rowA)[(0 * NTX + tx) * NTY + ty] = make_double2(th1[0][0], th1[0][1]);
+        reinterpret_cast<double2*>(rowA)[(1 * NTX + tx) * NTY + ty] = make_double2(th1[0][2], th1[0][3]);
         __syncthreads();
         double S[TX][TY];
         {
             double rc[TX], rr[TY];
-#pragma unroll
-            for (int i = 0; i < TX; ++i) rc[i] = colA[(i * NTX + tx) * NTY + tyR];
-#pragma unroll
-            for (int j = 0; j < TY; ++j) rr[j] = rowA[(j * NTX + txD) * NTY + ty];
+            {
+                const double2 c = reinterpret_cast<const double2*>(colA)[tx * NTY + tyR];
+                const double2 q0 = reinterpret_cast<const double2*>(rowA)[(0 * NTX + txD) * NTY + ty];
+                const double2 q1 = reinterpret_cast<const double2*>(rowA)[(1 * NTX + txD) * NTY + ty];
+                rc[0] = c.x; rc[1] = c.y; rr[0] = q0.x; rr[1] = q0.y; rr[2] = q1.x; rr[3] = q1.y;
+            }
 #pragma unroll
             for (int i = 0; i < TX; ++i)
 #pragma unroll
@@ -341,16 +343,17 @@ k_leapfrog_multi(MultiArgs a) {
                     S[i][j] = fast_sin(th0[i][j] - th1[i][j] - right + down);
                 }
         }
-#pragma unroll
-        for (int i = 0; i < TX; ++i) colB[(i * NTX + tx) * NTY + ty] = S[i][TY - 1];
-#pragma unroll
-        for (int j = 0; j < TY; ++j) rowB[(j * NTX + tx) * NTY + ty] = S[TX - 1][j];
+        reinterpret_cast<double2*>(colB)[tx * NTY + ty] = make_double2(S[0][TY - 1], S[1][TY - 1]);
+        reinterpret_cast<double2*>(rowB)[(0 * NTX + tx) * NTY + ty] = make_double2(S[TX - 1][0], S[TX - 1][1]);
+        reinterpret_cast<double2*>(rowB)[(1 * NTX + tx) * NTY + ty] = make_double2(S[TX - 1][2], S[TX - 1][3]);
         __syncthreads();
         double lc[TX], ur[TY];
-#pragma unroll
-        for (int i = 0; i < TX; ++i) lc[i] = colB[(i * NTX + tx) * NTY + tyL];
-#pragma unroll
-        for (int j = 0; j < TY; ++j) ur[j] = rowB[(j * NTX + txU) * NTY + ty];
+        {
+            const double2 c = reinterpret_cast<const double2*>(colB)[tx * NTY + tyL];
+            const double2 q0 = reinterpret_cast<const double2*>(rowB)[(0 * NTX + txU) * NTY + ty];
+            const double2 q1 = reinterpret_cast<const double2*>(rowB)[(1 * NTX + txU) * NTY + ty];
+            lc[0] = c.x; lc[1] = c.y; ur[0] = q0.x; ur[1] = q0.y; ur[2] = q1.x; ur[3] = q1.y;
+        }
 #pragma unroll
         for (int i = 0; i < TX; ++i)
 #pragma unroll
@@ -778,18 +781,47 @@ k_traj_resident(TrajArgs a) {
     for (int i = tid; i < kLogTabN; i += NT) ltab[i] = kLogTab[i];
     __syncthreads();
 
+    // Edge exchange through shared memory.  With 2 x 4 tiles the column edge (2 values) is one double2 at
+    // [tx][ty] and the row edge (4 values) two double2 at [jp][tx][ty]: 3 STS.128 + 3 LDS.128 per exchange
+    // instead of 6 + 6 64-bit accesses, lanes 16 bytes apart (conflict-free).  Other tile shapes keep the
+    // scalar layout.
+    constexpr bool VEC = (TX == 2 && TY == 4);
+    auto put_edges = [&](double* col, double* row, const double (&cv)[TX], const double (&rv)[TY]) {
+        if constexpr (VEC) {
+            reinterpret_cast<double2*>(col)[tx * NTY + ty] = make_double2(cv[0], cv[1]);
+            reinterpret_cast<double2*>(row)[(0 * NTX + tx) * NTY + ty] = make_double2(rv[0], rv[1]);
+            reinterpret_cast<double2*>(row)[(1 * NTX + tx) * NTY + ty] = make_double2(rv[2], rv[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < TX; ++i) col[(x0 + i) * NTY + ty] = cv[i];
+#pragma unroll
+            for (int j = 0; j < TY; ++j) row[(tx * TY + j) * NTY + ty] = rv[j];
+        }
+    };
+    auto get_edges = [&](const double* col, const double* row, int tyN, int txN, double (&cv)[TX], double (&rv)[TY]) {
+        if constexpr (VEC) {
+            const double2 c = reinterpret_cast<const double2*>(col)[tx * NTY + tyN];
+            const double2 r0 = reinterpret_cast<const double2*>(row)[(0 * NTX + txN) * NTY + ty];
+            const double2 r1 = reinterpret_cast<const double2*>(row)[(1 * NTX + txN) * NTY + ty];
+            cv[0] = c.x; cv[1] = c.y; rv[0] = r0.x; rv[1] = r0.y; rv[2] = r1.x; rv[3] = r1.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < TX; ++i) cv[i] = col[(x0 + i) * NTY + tyN];
+#pragma unroll
+            for (int j = 0; j < TY; ++j) rv[j] = row[(txN * TY + j) * NTY + ty];
+        }
+    };
     auto publish_theta = [&]() {
+        double cv[TX], rv[TY];
 #pragma unroll
-        for (int i = 0; i < TX; ++i) colA[(x0 + i) * NTY + ty] = th0[i][0];
+        for (int i = 0; i < TX; ++i) cv[i] = th0[i][0];
 #pragma unroll
-        for (int j = 0; j < TY; ++j) rowA[(tx * TY + j) * NTY + ty] = th1[0][j];
+        for (int j = 0; j < TY; ++j) rv[j] = th1[0][j];
+        put_edges(colA, rowA, cv, rv);
     };
     auto plaquettes = [&](double (&P)[TX][TY]) {   // call after publish_theta + __syncthreads
         double rc[TX], rr[TY];
-#pragma unroll
-        for (int i = 0; i < TX; ++i) rc[i] = colA[(x0 + i) * NTY + tyR];
-#pragma unroll
-        for (int j = 0; j < TY; ++j) rr[j] = rowA[(txD * TY + j) * NTY + ty];
+        get_edges(colA, rowA, tyR, txD, rc, rr);
 #pragma unroll
         for (int i = 0; i < TX; ++i)
 #pragma unroll
@@ -874,16 +906,17 @@ k_traj_resident(TrajArgs a) {
             for (int i = 0; i < TX; ++i)
 #pragma unroll
                 for (int j = 0; j < TY; ++j) S[i][j] = fast_sin(S[i][j]);
+            {
+                double cv[TX], rv[TY];
 #pragma unroll
-            for (int i = 0; i < TX; ++i) colB[(x0 + i) * NTY + ty] = S[i][TY - 1];
+                for (int i = 0; i < TX; ++i) cv[i] = S[i][TY - 1];
 #pragma unroll
-            for (int j = 0; j < TY; ++j) rowB[(tx * TY + j) * NTY + ty] = S[TX - 1][j];
+                for (int j = 0; j < TY; ++j) rv[j] = S[TX - 1][j];
+                put_edges(colB, rowB, cv, rv);
+            }
             __syncthreads();
             double lc[TX], ur[TY];
-#pragma unroll
-            for (int i = 0; i < TX; ++i) lc[i] = colB[(x0 + i) * NTY + tyL];
-#pragma unroll
-            for (int j = 0; j < TY; ++j) ur[j] = rowB[(txU * TY + j) * NTY + ty];
+            get_edges(colB, rowB, tyL, txU, lc, ur);
 #pragma unroll
             for (int i = 0; i < TX; ++i)
 #pragma unroll
