@@ -249,14 +249,9 @@ constexpr int kTileStages = 3;
 #ifndef U1_TILE_FWD_ROWS
 #define U1_TILE_FWD_ROWS 2
 #endif
-// Measured on B200 (rnet3, 342 chains, one force; profiles/r01_ft_variants_epilogue.log): baseline 18.76 ms;
-// CCTL prefetch 20.49; row-batched operand loads 23.33; cp.async table 18.61 -> only the last one is on.
-#ifndef U1_EPI_PREFETCH      // L2 prefetch of the epilogue operands before the channel loop
-#define U1_EPI_PREFETCH 0
-#endif
-#ifndef U1_EPI_BATCH         // epilogue operands loaded one output row at a time
-#define U1_EPI_BATCH 0
-#endif
+// Epilogue variants measured on B200 (profiles/r01_ft_variants_epilogue.log): an L2 prefetch (CCTL.E.PF2) of the
+// epilogue operands and row-batched operand loads were both slower and are gone; the two switches below
+// remain as A/B knobs (defaults = the faster setting).
 #ifndef U1_ADD_AT_START      // skip operand folded into the accumulator start values: 1 forward layers, 2 reverse layers too
 #define U1_ADD_AT_START 2
 #endif
@@ -324,16 +319,6 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
             acc[r][o] = (EPI == EPI_BWD) ? 0.0 : p.b[o];
             if (U1_ADD_AT_START && (EPI != EPI_BWD || U1_ADD_AT_START > 1) && add) acc[r][o] += add[ob + (size_t)o * V + (size_t)r * LL];
         }
-    if (U1_EPI_PREFETCH && (threadIdx.x & 15) == 0) { // one request per 128-byte line
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-            for (int o = 0; o < COUT; ++o) {
-                const size_t idx = ob + (size_t)o * V + (size_t)r * LL;
-                if (add) asm volatile("prefetch.global.L2 [%0];" ::"l"(add + idx));
-                if (EPI == EPI_BWD && mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul + idx));
-            }
-    }
 #pragma unroll 1
     for (int c = 0; c < CIN; ++c) {
         if (c + kTileStages - 1 <= CIN) asm volatile("cp.async.wait_group %0;" ::"n"(kTileStages - 2));
@@ -360,45 +345,28 @@ k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict
                     for (int r = 0; r < ROWS; ++r) acc[r][o] = fma(wv, v[i + r][j], acc[r][o]);
                 }
     }
-    // Epilogue operands (skip connection, GELU') were written several launches ago and come from DRAM:
-    // they were prefetched into L2 before the channel loop and are loaded one output row at a time
-    // (COUT independent loads in flight) instead of one exposed latency per value.
+    // Epilogue.  The skip operand is already inside acc (U1_ADD_AT_START); GELU' of the reverse layers is
+    // loaded here, interleaved by the compiler with the stores of the previous values.
+    constexpr bool kAddHere = !(U1_ADD_AT_START && (EPI != EPI_BWD || U1_ADD_AT_START > 1));
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const size_t rb = ob + (size_t)r * LL;
-        double ad[COUT], ml[COUT];
-#if U1_EPI_BATCH
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
-            ad[o] = (add && !(U1_ADD_AT_START && (EPI != EPI_BWD || U1_ADD_AT_START > 1))) ? add[rb + (size_t)o * V] : 0.0;
-            ml[o] = (EPI == EPI_BWD && mul) ? mul[rb + (size_t)o * V] : 1.0;
-        }
-#endif
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            const size_t idx = rb + (size_t)o * V;
+            const size_t idx = ob + (size_t)o * V + (size_t)r * LL;
             if (EPI == EPI_BWD) {
-#if !U1_EPI_BATCH
-                ad[o] = (add && U1_ADD_AT_START < 2) ? add[idx] : 0.0;
-                ml[o] = (EPI == EPI_BWD && mul) ? mul[idx] : 1.0;
-#endif
                 double rv = acc[r][o];
-                if (add && U1_ADD_AT_START < 2) rv += ad[o];
-                if (mul) rv *= ml[o];
+                if (kAddHere && add) rv += add[idx];
+                if (mul) rv *= mul[idx];
                 out[idx] = rv;
             } else {
-#if !U1_EPI_BATCH
-                ad[o] = (add && !U1_ADD_AT_START) ? add[idx] : 0.0;
-#endif
                 double z = acc[r][o];
-                if (add && !U1_ADD_AT_START) z += ad[o];
+                if (kAddHere && add) z += add[idx];
                 double g, d;
                 gelu_and_grad(s_tab, z, g, d);
                 out[idx] = g;
                 if (dout) dout[idx] = d;
             }
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------

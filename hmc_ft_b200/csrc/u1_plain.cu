@@ -382,151 +382,6 @@ k_leapfrog_multi(MultiArgs a) {
     }
 }
 
-// Persistent, prefetching variant (EW = 32): CTAs loop over windows (static round-robin) and every thread
-// stages the 16 double2 of its OWN 2 x 4 sites of the next window into a private shared-memory slot with
-// cp.async (L2 -> smem, no registers) before it starts the 4 leapfrog steps of the current window, so the
-// HBM read of window w+1 overlaps the FP64 work of window w (in the plain variant the two CTAs of an SM
-// load, compute and store in lockstep: 8.3 us per window wave = 4.9 us of memory + 3.1 us of math).  The
-// slots are thread-private ([k][tid] layout, conflict-free), so no barrier is needed for the staged data:
-// cp.async.wait_group by the owning thread is enough.  Results are bit-identical to k_leapfrog_multi.
-template <int EW>
-__global__ void __launch_bounds__((kMsE / 2) * (EW / 4), 512 / ((kMsE / 2) * (EW / 4)))
-k_leapfrog_multi_pf(MultiArgs a, int windows_per_chain, int total_windows) {
-    constexpr int L = kMsE, TX = 2, TY = 4, NTX = L / TX, NTY = EW / TY, OW = EW - 2 * kMsHalo, NT = NTX * NTY;
-    extern __shared__ __align__(16) double dsm[];
-    double* colA = dsm;
-    double* rowA = colA + L * NTY;
-    double* colB = rowA + NTX * TY * NTY;
-    double* rowB = colB + L * NTY;
-    double2* stage = reinterpret_cast<double2*>(rowB + NTX * TY * NTY);      // [16][NT]
-
-    const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
-    const int x0 = tx * TX, y0 = ty * TY;
-    const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
-    const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
-    const size_t V = (size_t)a.Lx * a.L;
-    const double kb = a.dt * a.beta;
-
-    // global offset of this thread's site (row i, first column) in window w; columns gy..gy+3 are contiguous
-    auto site_base = [&](int w, int i, int& tile_x, int& tile_y) -> size_t {
-        const int b = w / windows_per_chain, t = w - b * windows_per_chain;
-        tile_x = t / a.tiles_y; tile_y = t - tile_x * a.tiles_y;
-        int gy = (tile_y * OW - kMsHalo + y0) % a.L; if (gy < 0) gy += a.L;
-        int gx = (tile_x * kMsOut - kMsHalo + x0 + i) % a.Lx; if (gx < 0) gx += a.Lx;
-        return (size_t)b * 2 * V + (size_t)gx * a.L + gy;
-    };
-    auto prefetch = [&](int w) {
-        int txx, tyy;
-#pragma unroll
-        for (int i = 0; i < TX; ++i) {
-            const size_t g = site_base(w, i, txx, tyy);
-#pragma unroll
-            for (int jp = 0; jp < TY / 2; ++jp) {
-                const int k = (i * (TY / 2) + jp) * 4;
-                const double* src[4] = {a.th + g + 2 * jp, a.th + g + V + 2 * jp, a.pi + g + 2 * jp, a.pi + g + V + 2 * jp};
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (k + f) * NT + tid);
-#ifdef U1_PF_CA
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[f]) : "memory");
-#else
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[f]) : "memory");
-#endif
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    int w = blockIdx.x;
-    if (w < total_windows) prefetch(w);
-    for (; w < total_windows; w += gridDim.x) {
-        double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < TX; ++i)
-#pragma unroll
-            for (int jp = 0; jp < TY / 2; ++jp) {
-                const int k = (i * (TY / 2) + jp) * 4, j = 2 * jp;
-                const double2 v0 = stage[(k + 0) * NT + tid], v1 = stage[(k + 1) * NT + tid];
-                const double2 q0 = stage[(k + 2) * NT + tid], q1 = stage[(k + 3) * NT + tid];
-                th0[i][j] = v0.x; th0[i][j + 1] = v0.y; th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
-                p0[i][j] = q0.x; p0[i][j + 1] = q0.y; p1[i][j] = q1.x; p1[i][j + 1] = q1.y;
-            }
-        // the slots are free again (this thread has its values in registers): stage the next window
-        if (w + (int)gridDim.x < total_windows) prefetch(w + gridDim.x);
-
-        for (int s = 0; s < a.ksteps; ++s) {
-            const double dr = (s == 0) ? a.first_drift : a.dt;
-#pragma unroll
-            for (int i = 0; i < TX; ++i)
-#pragma unroll
-                for (int j = 0; j < TY; ++j) {
-                    th0[i][j] = fma(dr, p0[i][j], th0[i][j]);
-                    th1[i][j] = fma(dr, p1[i][j], th1[i][j]);
-                }
-#pragma unroll
-            for (int i = 0; i < TX; ++i) colA[(i * NTX + tx) * NTY + ty] = th0[i][0];
-#pragma unroll
-            for (int j = 0; j < TY; ++j) rowA[(j * NTX + tx) * NTY + ty] = th1[0][j];
-            __syncthreads();
-            double S[TX][TY];
-            {
-                double rc[TX], rr[TY];
-#pragma unroll
-                for (int i = 0; i < TX; ++i) rc[i] = colA[(i * NTX + tx) * NTY + tyR];
-#pragma unroll
-                for (int j = 0; j < TY; ++j) rr[j] = rowA[(j * NTX + txD) * NTY + ty];
-#pragma unroll
-                for (int i = 0; i < TX; ++i)
-#pragma unroll
-                    for (int j = 0; j < TY; ++j) {
-                        const double right = (j + 1 < TY) ? th0[i][j + 1] : rc[i];
-                        const double down = (i + 1 < TX) ? th1[i + 1][j] : rr[j];
-                        S[i][j] = fast_sin(th0[i][j] - th1[i][j] - right + down);
-                    }
-            }
-#pragma unroll
-            for (int i = 0; i < TX; ++i) colB[(i * NTX + tx) * NTY + ty] = S[i][TY - 1];
-#pragma unroll
-            for (int j = 0; j < TY; ++j) rowB[(j * NTX + tx) * NTY + ty] = S[TX - 1][j];
-            __syncthreads();
-            double lc[TX], ur[TY];
-#pragma unroll
-            for (int i = 0; i < TX; ++i) lc[i] = colB[(i * NTX + tx) * NTY + tyL];
-#pragma unroll
-            for (int j = 0; j < TY; ++j) ur[j] = rowB[(j * NTX + txU) * NTY + ty];
-#pragma unroll
-            for (int i = 0; i < TX; ++i)
-#pragma unroll
-                for (int j = 0; j < TY; ++j) {
-                    const double left = (j > 0) ? S[i][j - 1] : lc[i];
-                    const double up = (i > 0) ? S[i - 1][j] : ur[j];
-                    p0[i][j] = fma(-kb, S[i][j] - left, p0[i][j]);
-                    p1[i][j] = fma(-kb, up - S[i][j], p1[i][j]);
-                }
-        }
-        // write back the inner block (clipped to the lattice for the last tile row / column)
-        const int ly = y0 - kMsHalo;
-#pragma unroll
-        for (int i = 0; i < TX; ++i) {
-            int tile_x, tile_y;
-            const size_t g = site_base(w, i, tile_x, tile_y);
-            const int lx = x0 + i - kMsHalo;
-            const bool keep = ly >= 0 && ly < OW && tile_y * OW + ly < a.L && lx >= 0 && lx < kMsOut && tile_x * kMsOut + lx < a.Lx;
-            if (keep) {
-#pragma unroll
-                for (int j = 0; j < TY; j += 2) {
-                    *reinterpret_cast<double2*>(a.tho + g + j) = make_double2(th0[i][j], th0[i][j + 1]);
-                    *reinterpret_cast<double2*>(a.tho + g + V + j) = make_double2(th1[i][j], th1[i][j + 1]);
-                    *reinterpret_cast<double2*>(a.pio + g + j) = make_double2(p0[i][j], p0[i][j + 1]);
-                    *reinterpret_cast<double2*>(a.pio + g + V + j) = make_double2(p1[i][j], p1[i][j + 1]);
-                }
-            }
-        }
-    }
-}
-
 static bool multi_supported(int Lx, int L) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("U1_MULTISTEP"); enabled = e ? atoi(e) : 1; }
@@ -557,27 +412,7 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
         constexpr int NTY = 8;
         constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
         a.tiles_y = (L + 24 - 1) / 24;
-        static int pf = -1;
-        if (pf < 0) { const char* e = getenv("U1_MULTISTEP_PF"); pf = e ? atoi(e) : 0; }   // measured slower (447 vs 306 us at L=4096): opt-in
-        const long long total = (long long)tiles_x * a.tiles_y * B;
-        if (pf && total < (1ll << 30)) {
-            constexpr size_t smem_pf = smem + (size_t)16 * 256 * sizeof(double2);      // + 64 KB of staging slots
-            static int slots = 0;                     // resident CTAs on the device (2 per SM when the carve-out allows)
-            if (slots == 0) {
-                cudaError_t e = cudaFuncSetAttribute(k_leapfrog_multi_pf<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pf);
-                if (e != cudaSuccess) return (int)e;
-                cudaFuncSetAttribute(k_leapfrog_multi_pf<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                int dev = 0, sms = 0, occ = 0;
-                cudaGetDevice(&dev);
-                if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_leapfrog_multi_pf<32>, 256, smem_pf) != cudaSuccess || occ < 1) occ = 1;
-                slots = sms * occ;
-            }
-            const int grid = (int)(total < (long long)slots ? total : (long long)slots);
-            k_leapfrog_multi_pf<32><<<grid, 256, smem_pf, st>>>(a, tiles_x * a.tiles_y, (int)total);
-        } else {
-            k_leapfrog_multi<32><<<dim3(tiles_x * a.tiles_y, B), 256, smem, st>>>(a);
-        }
+        k_leapfrog_multi<32><<<dim3(tiles_x * a.tiles_y, B), 256, smem, st>>>(a);
     }
     count_launch();
     U1_CHECK_LAUNCH();

@@ -19,4 +19,4 @@ e0.record()
 for _ in range(50): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 50
-print(f"PF={os.environ.get('U1_MULTISTEP_PF','0 (default)')} Lx={Lx} L={L}: {ms*1e3:.1f} us per 4 steps -> {Lx*L*4/ms/1e6:.1f} G site-updates/s, {Lx*L*4*64/ms/1e9:.2f} TB/s algorithmic")
+print(f"Lx={Lx} L={L}: {ms*1e3:.1f} us per 4 steps -> {Lx*L*4/ms/1e6:.1f} G site-updates/s, {Lx*L*4*64/ms/1e9:.2f} TB/s algorithmic")
