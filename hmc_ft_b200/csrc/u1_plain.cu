@@ -589,31 +589,48 @@ struct TrajArgs {
     double* out_dH; int32_t* out_acc; double* out_H; double* out_plaq; double* out_topo;
 };
 
-template <int L, int TX, int TY>
+// PF = persistent CTAs with a TMA bulk prefetch: the grid is one CTA per SM, every CTA walks chains
+// b = blockIdx.x, blockIdx.x + gridDim.x, ... and, as soon as its threads hold the current chain in
+// registers, one thread starts `cp.async.bulk` (UBLKCP) of the NEXT chain's 2*V doubles into a shared-memory
+// stage, completion on an mbarrier; the next trajectory then starts from shared memory instead of
+// waiting on HBM with an otherwise idle SM (one CTA fills the register file, so nothing else hides it).
+template <int L, int TX, int TY, bool PF>
 __global__ void __launch_bounds__((L / TX) * (L / TY))
 k_traj_resident(TrajArgs a) {
     constexpr int NTX = L / TX, NTY = L / TY, NT = NTX * NTY, V = L * L;
     static_assert(NT % 32 == 0 && TY % 2 == 0, "tile config");
-    extern __shared__ double dsm[];
+    extern __shared__ __align__(16) double dsm[];
     double* colA = dsm;                       // theta0' at (x, first column of tile ty): [x][ty]
     double* rowA = colA + L * NTY;            // theta1' at (first row of tile tx, y): [tx][j][ty]
     double* colB = rowA + NTX * TY * NTY;     // sinP at (x, last column of tile ty)
     double* rowB = colB + L * NTY;            // sinP at (last row of tile tx, y)
     double* red = rowB + NTX * TY * NTY;      // 3*32 reduction scratch
     LogTabEntry* ltab = reinterpret_cast<LogTabEntry*>(red + 96);   // Box-Muller log table (2 KB)
+    double* stage = reinterpret_cast<double*>(ltab + kLogTabN);       // PF: next chain's theta [2][L][L]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage + 2 * V);      // PF: completion barrier of the bulk copy
 
     const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
     const int x0 = tx * TX, y0 = ty * TY;
     const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
     const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
-    const int b = blockIdx.x;
-    double* g0 = a.theta + (size_t)b * 2 * V;
-    double* g1 = g0 + V;
-    const PhiloxKey key = chain_key(a.seed, a.chain0 + b);
     const double beta = a.beta, dt = a.dt, kb = a.dt * a.beta;
 
     double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
     for (int i = tid; i < kLogTabN; i += NT) ltab[i] = kLogTab[i];
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbar);
+    auto prefetch_chain = [&](int bn) {              // thread 0 only
+        constexpr unsigned kBytes = 2u * V * (unsigned)sizeof(double);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(kBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(stage)), "l"(a.theta + (size_t)bn * 2 * V), "r"(kBytes), "r"(mbar_s)
+                     : "memory");
+    };
+    if (PF && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((int)blockIdx.x < a.B) prefetch_chain(blockIdx.x);
+    }
+    unsigned parity = 0;
     __syncthreads();
 
     // Edge exchange through shared memory.  With 2 x 4 tiles the column edge (2 values) is one double2 at
@@ -688,19 +705,38 @@ k_traj_resident(TrajArgs a) {
         block_sum<3>(v, red);
     };
 
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    double* g0 = a.theta + (size_t)b * 2 * V;
+    double* g1 = g0 + V;
+    const PhiloxKey key = chain_key(a.seed, a.chain0 + b);
     for (int t = 0; t < a.n_traj; ++t) {
         const uint64_t traj = a.traj0 + (uint64_t)t;
         // ---- load state, draw momenta ----
+        const bool staged = PF && t == 0;
+        if (staged) {                                 // wait for the bulk copy of this chain
+            asm volatile("{\n.reg .pred P1;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}"
+                         ::"r"(mbar_s), "r"(parity) : "memory");
+            parity ^= 1u;
+        }
+        const double* s0 = staged ? stage : g0;
+        const double* s1 = staged ? stage + V : g1;
 #pragma unroll
         for (int i = 0; i < TX; ++i)
 #pragma unroll
             for (int j = 0; j < TY; j += 2) {
                 const int g = (x0 + i) * L + y0 + j;
-                const double2 v0 = *reinterpret_cast<const double2*>(g0 + g);
-                const double2 v1 = *reinterpret_cast<const double2*>(g1 + g);
+                const double2 v0 = *reinterpret_cast<const double2*>(s0 + g);
+                const double2 v1 = *reinterpret_cast<const double2*>(s1 + g);
                 th0[i][j] = v0.x; th0[i][j + 1] = v0.y;
                 th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
             }
+        if (staged) {                                 // every thread has its sites: the stage is free for the next chain
+            __syncthreads();
+            if (tid == 0 && b + (int)gridDim.x < a.B) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                prefetch_chain(b + gridDim.x);
+            }
+        }
         if (a.pi_inject) {
             const double* q0 = a.pi_inject + ((size_t)t * a.B + b) * 2 * V;
             const double* q1 = q0 + V;
@@ -796,6 +832,7 @@ k_traj_resident(TrajArgs a) {
             if (a.out_topo) a.out_topo[o] = f[1];
         }
     }
+    }
 }
 
 // ---- training-loss reduction (field_trans_opt.py:452-458): sum |a-b|^p for p = 2,4,6,8 over n elements ----
@@ -878,19 +915,38 @@ __global__ void __launch_bounds__(256) k_autocorr(const double* __restrict__ top
 
 static bool resident_supported(int L) { return L == 8 || L == 16 || L == 32 || L == 64; }
 
-template <int L, int TX, int TY>
-static int launch_resident_t(const TrajArgs& a, cudaStream_t st) {
+template <int L, int TX, int TY, bool PF>
+static int launch_resident_pf(const TrajArgs& a, cudaStream_t st) {
     constexpr int NTX = L / TX, NTY = L / TY;
-    constexpr size_t smem = (size_t)(2 * (L * NTY + NTX * TY * NTY) + 3 * 32) * sizeof(double) + kLogTabN * sizeof(LogTabEntry);
+    constexpr size_t smem = (size_t)(2 * (L * NTY + NTX * TY * NTY) + 3 * 32) * sizeof(double) + kLogTabN * sizeof(LogTabEntry) +
+                            (PF ? (size_t)2 * L * L * sizeof(double) + 16 : 0);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_traj_resident<L, TX, TY>,
+        cudaError_t e = cudaFuncSetAttribute(k_traj_resident<L, TX, TY, PF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    k_traj_resident<L, TX, TY><<<a.B, NTX * NTY, smem, st>>>(a);
+    int grid = a.B;
+    if (PF) {                                         // persistent: as many CTAs as can be resident at once
+        static int slots = 0;
+        if (slots == 0) {
+            int dev = 0, sms = 0, occ = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traj_resident<L, TX, TY, PF>, NTX * NTY, smem) != cudaSuccess || occ < 1) occ = 1;
+            slots = sms * occ;
+        }
+        if (grid > slots) grid = slots;
+    }
+    k_traj_resident<L, TX, TY, PF><<<grid, NTX * NTY, smem, st>>>(a);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
+}
+template <int L, int TX, int TY>
+static int launch_resident_t(const TrajArgs& a, cudaStream_t st) {
+    static int pf = -1;                               // U1_RESIDENT_PF=0: one CTA per chain, loads from global
+    if (pf < 0) { const char* e = getenv("U1_RESIDENT_PF"); pf = e ? atoi(e) : 1; }
+    return pf ? launch_resident_pf<L, TX, TY, true>(a, st) : launch_resident_pf<L, TX, TY, false>(a, st);
 }
 
 static int launch_resident(const TrajArgs& a, int L, cudaStream_t st) {

@@ -290,3 +290,44 @@ def test_multistep_kernel_bit_identical_to_single_steps(hb, Lx, L, B):
         c_t, d_t, c_p, d_p = d_t, c_t, d_p, c_p
     torch.cuda.synchronize()
     assert torch.equal(res_t, c_t) and torch.equal(res_p, c_p)
+
+
+def test_full_size_size_independent_properties(hb):
+    """BASELINE configs[1] shape (L=64, beta=6, 4096 chains): properties that need no oracle at this size.
+    (1) the leapfrog map is reversible: integrate, flip the momenta, integrate again -> the start (mod 2 pi);
+    (2) energy error scales like dt^2 (halving dt at fixed trajectory length divides <|dH|> by ~4);
+    (3) a chain's result does not depend on its neighbours in the batch (chains 100..103 alone == inside the batch);
+    (4) the resident and the streaming kernels agree on dH to round-off with injected momenta."""
+    L, B, beta = 64, 4096, 6.0
+    g = torch.Generator().manual_seed(2024)
+    th = ((torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * 0.6).cuda()
+    pi = torch.randn(B, 2, L, L, generator=g, dtype=torch.float64).cuda()
+    h = hb.HMC_U1(L, beta, 0, 50, 0.06, n_chains=B, if_tune_step_size=False)
+    t1, p1 = h.leapfrog(th, pi)
+    t2, p2 = h.leapfrog(t1, -p1)
+    d = torch.remainder(t2 - th + math.pi, 2 * math.pi) - math.pi
+    assert d.abs().max().item() < 1e-10 and (p2 + pi).abs().max().item() < 1e-9
+    # (2) dt^2 scaling of the energy error, same momenta
+    r1 = h.trajectories(th.clone(), 1, pi=pi[None].contiguous(), u=torch.zeros(B, dtype=torch.float64, device="cuda"))
+    h2 = hb.HMC_U1(L, beta, 0, 100, 0.03, n_chains=B, if_tune_step_size=False)
+    r2 = h2.trajectories(th.clone(), 1, pi=pi[None].contiguous(), u=torch.zeros(B, dtype=torch.float64, device="cuda"))
+    ratio = r1["dH"].abs().mean().item() / r2["dH"].abs().mean().item()
+    assert 3.0 < ratio < 5.5, ratio
+    # (3) batch independence at full size
+    sub = slice(100, 104)
+    hs = hb.HMC_U1(L, beta, 0, 50, 0.06, n_chains=4, if_tune_step_size=False, chain_offset=100)
+    hf = hb.HMC_U1(L, beta, 0, 50, 0.06, n_chains=B, if_tune_step_size=False)      # fresh trajectory counter
+    ta, tb = th.clone(), th[sub].clone()
+    ra = hf.trajectories(ta, 2)
+    rb = hs.trajectories(tb, 2)
+    assert torch.equal(ta[sub], tb) and torch.equal(ra["dH"][:, sub], rb["dH"])
+    # (4) resident vs streaming path, injected draws
+    hk = hb.HMC_U1(L, beta, 0, 50, 0.06, n_chains=64, if_tune_step_size=False, kernel_path=1)
+    h0 = hb.HMC_U1(L, beta, 0, 50, 0.06, n_chains=64, if_tune_step_size=False)
+    u0 = torch.full((64,), 0.5, dtype=torch.float64, device="cuda")
+    pa = pi[None, :64].contiguous()
+    x0, x1 = th[:64].clone(), th[:64].clone()
+    q0 = h0.trajectories(x0, 1, pi=pa, u=u0)
+    q1 = hk.trajectories(x1, 1, pi=pa, u=u0)
+    assert (q0["dH"] - q1["dH"]).abs().max().item() < 1e-8 and torch.equal(q0["accept"], q1["accept"])
+    assert torch.equal(q0["topo"], q1["topo"]) and (q0["plaq"] - q1["plaq"]).abs().max().item() < 1e-12
