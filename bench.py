@@ -279,6 +279,17 @@ def run_ours(args):
             extra["ft"] = bench_ft(args, rank, world, dev, time_steps)
         except Exception as e:      # FT numbers are secondary to the contract line
             extra["ft"] = {"error": f"{type(e).__name__}: {e}"}
+        # the other FT configurations SURVEY §8(d) names (one timed trajectory each): the smaller shipped CNNs
+        # at L=64 beta=6 and BASELINE configs[2] (L=32 beta=3, rnet3 weights trained at beta=3)
+        extra["ft_other"] = []
+        for arch, L_o, beta_o in (("simple", 64, 6.0), ("rnet1", 64, 6.0), ("rnet3", 32, 3.0)):
+            try:
+                r = bench_ft(args, rank, world, dev, time_steps, arch=arch, L=L_o, beta=beta_o, steps=1, warmup=1)
+                extra["ft_other"].append({"metric": r["metric"], "value": r["value"], "unit": r["unit"],
+                                          "ms_per_step": r["ms_per_step"], "accept_rate": r["accept_rate"],
+                                          "fp64_frac": r["roofline"]["frac"], "tflops": r["roofline"]["achieved"]})
+            except Exception as e:
+                extra["ft_other"].append({"config": f"{arch} L={L_o} beta={beta_o}", "error": f"{type(e).__name__}: {e}"})
 
     if not args.no_slab:
         try:

@@ -236,8 +236,9 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 // channels stream in while the current one feeds the DFMAs and the window reads become LDS.
 // Inner loop measured at 72.9 % (ROWS=2) / 76.6 % (ROWS=4) of the DFMA peak against 64 % for the
 // direct-load kernel (tools/microbench/conv_variants.cu, profiles/conv_variants5.log).  Forward
-// layers use ROWS=2 (24 inlined GELU evaluations keep the code in the instruction cache), reverse
-// layers ROWS=4.  Same epilogues and launch protocol as k_conv.
+// layers use ROWS=2 with <= 102 registers (minBlocks 5; with the v2 GELU table 5 and 6 measure the same,
+// 4 -- 128 registers -- makes ptxas schedule the ROWS=2 body 30 % slower; ROWS=4 at minBlocks 4 is within
+// 2 % of ROWS=2), reverse layers ROWS=4.  Same epilogues and launch protocol as k_conv.
 // ---------------------------------------------------------------------------------------
 constexpr int kTileStages = 3;
 #ifndef U1_TILE_FWD_MINB
@@ -1058,9 +1059,8 @@ static int tile_path_enabled() {          // U1FT_TILE: 0 off, 1 reverse layers 
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
-    // Measured in the full force (342 chains): reverse layers 135 vs 161 us (ncu), whole force 22.0 vs
-    // 19.8 TFLOP/s with both directions tiled.  The forward variant needs the 80-register cap
-    // (__launch_bounds__ minBlocks 6): at 96 registers ptxas schedules it 30 % slower than the direct kernel.
+    // Measured in the full force (342 chains): reverse layers 135 vs 161 us (ncu), forward layers 161 vs 228 us
+    // against the direct kernel; the register caps of the tiled kernels are the U1_TILE_*_MINB knobs above.
     if (tile_path_enabled() && (EPI == EPI_BWD || tile_path_enabled() > 1)) {
         if (L == 64) return launch_conv_tile<64, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
         if (L == 32) return launch_conv_tile<32, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);

@@ -133,9 +133,10 @@ class HMC_U1:
         self.traj_counter += n_traj
         return out
 
-    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices: int = 8):
+    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices=8):
         """One Metropolis step of a HOST-resident batch [B,2,L,L] (fp64, ideally pinned): the batch is cut
-        into `n_slices` slices whose H2D copy, trajectory kernel and D2H copy run on rotating CUDA
+        into `n_slices` slices (or, with n_slices="tapered", ten slices of 1/32 .. 1/4 .. 1/32 of the batch)
+        whose H2D copy, trajectory kernel and D2H copy run on rotating CUDA
         streams, so the two PCIe directions and the SMs overlap.  Returns (theta_out_host, obs_host)
         with obs_host = pinned fp64 [4,B] = (accept, H, plaq, topo).  Chains keep their global Philox
         ids (chain_offset + index), so the result equals the resident path bit for bit."""
@@ -147,8 +148,19 @@ class HMC_U1:
             theta_host = theta_host.pin_memory()
         if out_host is None:
             out_host = torch.empty_like(theta_host).pin_memory()
-        n_slices = max(1, min(n_slices, B))
-        key = (B, L, n_slices)
+        if n_slices in (0, "tapered"):
+            # small slices at both ends, big ones in the middle: the pipeline fill (first H2D) and drain (last
+            # kernel + D2H) shrink from 1/8 to 1/32 of the batch while the launch count stays ~10
+            frac = [1, 1, 2, 4, 8, 8, 4, 2, 1, 1]
+            cuts = [0]
+            for f in frac:
+                cuts.append(cuts[-1] + f)
+            bounds = sorted({(c * B) // cuts[-1] for c in cuts})
+        else:
+            n_slices = max(1, min(int(n_slices), B))
+            bounds = [(i * B) // n_slices for i in range(n_slices + 1)]
+        n_slices = len(bounds) - 1
+        key = (B, L, tuple(bounds))
         st = getattr(self, "_host_state", None)
         if st is None or st["key"] != key:
             st = {"key": key, "dev": torch.empty((B, 2, L, L), dtype=torch.float64, device=dev),
@@ -158,9 +170,9 @@ class HMC_U1:
                   "streams": [torch.cuda.Stream(device=dev) for _ in range(min(3, n_slices))]}
             self._host_state = st
         cur = torch.cuda.current_stream(dev)
-        bounds = [(i * B) // n_slices for i in range(n_slices + 1)]
+        widest = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
         with torch.cuda.device(dev):
-            ws_all = [WS.get(dev, self._lib.u1_workspace_bytes(bounds[1] - bounds[0] + 1, L), f"host{j}")
+            ws_all = [WS.get(dev, self._lib.u1_workspace_bytes(widest + 1, L), f"host{j}")
                       for j in range(len(st["streams"]))]
             for i in range(n_slices):
                 a, b = bounds[i], bounds[i + 1]

@@ -197,6 +197,10 @@ def test_step_host_pipeline_matches_resident(hb):
     r2 = h1.trajectories(d, 1)
     torch.cuda.synchronize()
     assert torch.equal(out2, d.cpu())
+    out3, _ = h2.step_host(out2, n_slices="tapered")       # small slices at both ends, same chain
+    r3 = h1.trajectories(d, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out3, d.cpu())
 
 
 def test_topological_susceptibility_matches_theory(hb):

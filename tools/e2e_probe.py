@@ -6,13 +6,14 @@ h = hb.HMC_U1(L, 6.0, 0, 50, 0.06, device="cpu", if_tune_step_size=False, n_chai
 th = ((torch.rand(B, 2, L, L, dtype=torch.float64) * 2 - 1) * math.pi).pin_memory()
 out = torch.empty_like(th).pin_memory()
 print("pinned:", th.is_pinned(), out.is_pinned(), th[0:512].is_pinned())
-def timed(fn, reps=5):
-    fn(); torch.cuda.synchronize()
+def timed(fn, reps=10):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(reps): fn()
+    for _ in range(reps): fn(); torch.cuda.current_stream().synchronize()
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / reps * 1e3
-for ns in (1, 2, 4, 8, 16, 32):
-    print("n_slices", ns, f"{timed(lambda: h.step_host(th, out, n_slices=ns)):.2f} ms")
-t0 = time.perf_counter(); h.step_host(th, out, n_slices=8); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-print(f"host-side issue time {1e3*(t1-t0):.2f} ms, total {1e3*(t2-t0):.2f} ms")
+for rep in range(2):
+    for ns in (4, 8, "tapered", 12, 16):
+        print("n_slices", ns, f"{timed(lambda: h.step_host(th, out, n_slices=ns)):.2f} ms")
