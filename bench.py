@@ -233,8 +233,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (k_traj_resident): one launch == one step here ----
     ach = su_per_step * BYTES_PER_SITE_UPDATE / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": 275.4e6, "traffic_source": "ncu --set full, dram__bytes_read.sum+dram__bytes_write.sum per launch "
-                                                       "(profiles/r01_ncu_full_k_traj_resident_v4.txt)",
+                "traffic": 273.3e6, "traffic_source": "ncu --set full, dram__bytes_read.sum+dram__bytes_write.sum per launch "
+                                                       "(profiles/r01_ncu_full_k_traj_resident_v5.txt)",
                 "algorithmic_bytes_per_launch": su_per_step * BYTES_PER_SITE_UPDATE,
                 "kernel": "k_traj_resident<64,2,4>", "peak_source": peak_src,
                 "note": "algorithmic bytes = 64 B x site-updates (SURVEY §8d); the kernel keeps theta,pi in "
