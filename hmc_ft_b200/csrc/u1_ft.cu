@@ -235,20 +235,22 @@ k_conv(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in
 // below, columns wrap inside the row) is staged by cp.async into a 3-deep ring, so the next two
 // channels stream in while the current one feeds the DFMAs and the window reads become LDS.
 // Inner loop measured at 72.9 % (ROWS=2) / 76.6 % (ROWS=4) of the DFMA peak against 64 % for the
-// direct-load kernel (tools/microbench/conv_variants.cu, profiles/conv_variants5.log).  Forward
-// layers use ROWS=2 with <= 102 registers (minBlocks 5; with the v2 GELU table 5 and 6 measure the same,
-// 4 -- 128 registers -- makes ptxas schedule the ROWS=2 body 30 % slower; ROWS=4 at minBlocks 4 is within
-// 2 % of ROWS=2), reverse layers ROWS=4.  Same epilogues and launch protocol as k_conv.
+// direct-load kernel (tools/microbench/conv_variants.cu, profiles/conv_variants5.log).  Both directions
+// use ROWS=4 at 128 registers (minBlocks 4).  Forward layers used ROWS=2 with <= 102 registers while the
+// GELU epilogue was expensive; with the v2 table and the skip operand at the accumulator start ROWS=4 is
+// 1.5 % faster in the whole force (interleaved A/B, profiles/r01_ft_variants_epilogue.log).  ROWS=2 needs
+// minBlocks 5 or 6 (<= 102 registers): at 128 registers ptxas schedules that body 30 % slower.
+// Same epilogues and launch protocol as k_conv.
 // ---------------------------------------------------------------------------------------
 constexpr int kTileStages = 3;
 #ifndef U1_TILE_FWD_MINB
-#define U1_TILE_FWD_MINB 5
+#define U1_TILE_FWD_MINB 4
 #endif
 #ifndef U1_TILE_BWD_MINB
 #define U1_TILE_BWD_MINB 4
 #endif
 #ifndef U1_TILE_FWD_ROWS
-#define U1_TILE_FWD_ROWS 2
+#define U1_TILE_FWD_ROWS 4
 #endif
 // Epilogue variants measured on B200 (profiles/r01_ft_variants_epilogue.log): an L2 prefetch (CCTL.E.PF2) of the
 // epilogue operands and row-batched operand loads were both slower and are gone; the two switches below
