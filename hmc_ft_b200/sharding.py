@@ -140,8 +140,8 @@ class SlabHMC:
         """One Metropolis step.  theta_own [2,Lx,L] (this rank's rows, contiguous fp64 on the device) is
         updated in place.  Returns 1-element device tensors dH, accept, H, plaq, topo (no host sync).
 
-        After two eager trajectories the whole step (about 60 kernel launches, the halo exchanges and the
-        two all-reduces) is captured once into a CUDA graph and replayed: the trajectory index lives in a
+        After two eager trajectories the whole step (about 25 kernel launches, the halo exchanges and the
+        all-reduce) is captured once into a CUDA graph and replayed: the trajectory index lives in a
         device counter that the graph increments (u1_momenta_rows_dev / u1_metropolis_sums_dev), so the
         replay draws fresh momenta and a fresh accept uniform.  `U1_SLAB_GRAPH=0`, an injected `u`, or a
         failed capture keep the eager path; with more than one rank the graph path is opt-in
