@@ -128,4 +128,14 @@ __device__ __forceinline__ double philox_accept_uniform(PhiloxKey k, uint64_t tr
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Per-device caches (occupancy slots, one-time function attributes) are indexed by the CURRENT device, so a
+// process that drives several GPUs gets one entry per GPU (include/u1hmc.h "Conventions").
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+constexpr int kMaxGridY = 65535;     // chains ride in gridDim.y in several kernels: callers slice above this
+
 }  // namespace u1

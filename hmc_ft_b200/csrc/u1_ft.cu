@@ -905,6 +905,12 @@ static int ensure_lanes(u1ft_handle_s* h) {
 constexpr uint32_t kMagic = 0x55314654u;  // "U1FT"
 
 static inline bool handle_ok(u1ft_handle_t h) { return h && h->magic == kMagic; }
+// The handle's GELU table lives on the device that was current at u1ft_create: every entry point must
+// run on that device (otherwise the kernels would dereference another GPU's memory).
+static inline bool handle_on_current_device(u1ft_handle_t h) {
+    int d = -1;
+    return cudaGetDevice(&d) == cudaSuccess && d == h->device;
+}
 static inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
 static inline int blocks_for(size_t n, int t) { return (int)((n + t - 1) / t); }
 static inline int ew_grid_ft(size_t n) {
@@ -959,7 +965,9 @@ static int chunk_chains(int B, int L) {
     long long nchunks = (B + c - 1) / c;
     if (nchunks < nl) nchunks = nl;
     if (nchunks % nl) nchunks += nl - nchunks % nl;
-    return (int)((B + nchunks - 1) / nchunks);
+    long long cc = (B + nchunks - 1) / nchunks;
+    if (cc > kMaxGridY) cc = kMaxGridY;                 // chains ride in gridDim.y of k_ft_update (small L, huge batches)
+    return (int)cc;
 }
 
 struct FtWs {
@@ -1037,11 +1045,12 @@ static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const do
     constexpr int ROWS = (EPI == EPI_BWD) ? 4 : U1_TILE_FWD_ROWS;
     constexpr int TILE = (ROWS * (kConvThreads / LL) + 2) * LL;
     constexpr size_t smem = ((size_t)kTileStages * TILE + (EPI == EPI_BWD ? 0 : kGeluTableDoubles)) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];      // function attributes are per device
+    const int dev_i = current_device();
+    if (!configured[dev_i].load(std::memory_order_acquire)) {
         const char* cv = getenv("U1FT_CARVEOUT");
         if (cv) cudaFuncSetAttribute(k_conv_tile<LL, ROWS, CIN, COUT, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-        configured = true;
+        configured[dev_i].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
@@ -1311,11 +1320,15 @@ int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_d
 int u1ft_destroy(u1ft_handle_t h) {
     if (!handle_ok(h)) return U1_ERR_HANDLE;
     h->magic = 0;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != h->device) cudaSetDevice(h->device);     // free on the device that owns the table / streams
     if (h->gelu_tab) cudaFree(h->gelu_tab);
     if (h->lanes_ready) {
         cudaEventDestroy(h->ev_fork);
         for (int l = 0; l < kLanes; ++l) { cudaStreamDestroy(h->lane[l]); cudaEventDestroy(h->ev_join[l]); }
     }
+    if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
     delete h;
     return U1_OK;
 }
@@ -1328,7 +1341,7 @@ size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward) {
 int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
                  int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1349,7 +1362,7 @@ int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double
 int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
                int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !delta || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1376,7 +1389,7 @@ int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
 int u1ft_coefficients(u1ft_handle_t h, const double* theta, int index, double* K,
                       int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !K || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1425,7 +1438,7 @@ int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* thet
                 double* logdet, int B, int L, double beta,
                 void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !S_ft || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1447,7 +1460,7 @@ int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* thet
 int u1ft_force(u1ft_handle_t h, const double* theta, double* force, double* S_ft,
                int B, int L, double beta, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !force || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1489,7 +1502,7 @@ int u1ft_leapfrog(u1ft_handle_t h, const double* theta_in, const double* pi_in,
                   double* theta_out, double* pi_out, int B, int L, double beta, double dt,
                   int n_steps, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
@@ -1515,7 +1528,7 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
                     double* out_topo, double* theta_ori_out,
                     void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
-    if (!handle_ok(h)) return U1_ERR_HANDLE;
+    if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);

@@ -6,6 +6,7 @@
 #include "u1_common.cuh"
 #include "u1_fastmath.cuh"
 #include <cstdlib>
+#include <atomic>
 
 namespace u1 {
 
@@ -245,11 +246,17 @@ static int launch_step(const StepArgs& in, int B, bool slab, cudaStream_t st) {
     if (a.L < 2 || (a.L & 1)) return U1_ERR_SHAPE;
     Tiling t = make_tiling(a.Lx, a.L);
     a.TR = t.TR; a.TC = t.TC; a.tiles_y = t.tiles_y;
-    dim3 grid(t.tiles_x * t.tiles_y, B);
-    if (slab) k_leapfrog_step<true><<<grid, kStepThreads, t.smem, st>>>(a);
-    else      k_leapfrog_step<false><<<grid, kStepThreads, t.smem, st>>>(a);
-    count_launch();
-    U1_CHECK_LAUNCH();
+    const size_t per = (size_t)2 * a.Lx * a.L;
+    for (int b0 = 0; b0 < B; b0 += kMaxGridY) {            // chains ride in gridDim.y (<= 65535 per launch)
+        const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+        StepArgs s = a;
+        s.th += (size_t)b0 * per; s.pi += (size_t)b0 * per; s.tho += (size_t)b0 * per; s.pio += (size_t)b0 * per;
+        dim3 grid(t.tiles_x * t.tiles_y, nb);
+        if (slab) k_leapfrog_step<true><<<grid, kStepThreads, t.smem, st>>>(s);
+        else      k_leapfrog_step<false><<<grid, kStepThreads, t.smem, st>>>(s);
+        count_launch();
+        U1_CHECK_LAUNCH();
+    }
     return U1_OK;
 }
 
@@ -401,21 +408,36 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
         constexpr int NTY = 16;
         constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
         a.tiles_y = (L + 56 - 1) / 56;
-        static bool configured = false;
-        if (!configured) {
+        static std::atomic<bool> configured[kMaxDevices];      // function attributes are per device
+        const int dev = current_device();
+        if (!configured[dev].load(std::memory_order_acquire)) {
             cudaError_t e = cudaFuncSetAttribute(k_leapfrog_multi<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            configured = true;
+            configured[dev].store(true, std::memory_order_release);
         }
-        k_leapfrog_multi<64><<<dim3(tiles_x * a.tiles_y, B), 512, smem, st>>>(a);
+        for (int b0 = 0; b0 < B; b0 += kMaxGridY) {
+            const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+            MultiArgs s = a;
+            const size_t off = (size_t)b0 * 2 * Lx * L;
+            s.th += off; s.pi += off; s.tho += off; s.pio += off;
+            k_leapfrog_multi<64><<<dim3(tiles_x * a.tiles_y, nb), 512, smem, st>>>(s);
+            count_launch();
+            U1_CHECK_LAUNCH();
+        }
     } else {
         constexpr int NTY = 8;
         constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY)) * sizeof(double);
         a.tiles_y = (L + 24 - 1) / 24;
-        k_leapfrog_multi<32><<<dim3(tiles_x * a.tiles_y, B), 256, smem, st>>>(a);
+        for (int b0 = 0; b0 < B; b0 += kMaxGridY) {
+            const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+            MultiArgs s = a;
+            const size_t off = (size_t)b0 * 2 * Lx * L;
+            s.th += off; s.pi += off; s.tho += off; s.pio += off;
+            k_leapfrog_multi<32><<<dim3(tiles_x * a.tiles_y, nb), 256, smem, st>>>(s);
+            count_launch();
+            U1_CHECK_LAUNCH();
+        }
     }
-    count_launch();
-    U1_CHECK_LAUNCH();
     return U1_OK;
 }
 
@@ -519,10 +541,14 @@ static inline int sum_blocks(int B, int Lx) { const int r = sum_rows_per_block(B
 static int launch_sums(const double* th, const double* th_dn, const double* pi, double* sums,
                        double* partial, int B, int Lx, int L, cudaStream_t st, size_t plane = 0, int dn_in_place = 0) {
     const int rpb = sum_rows_per_block(B, Lx), nblk = (Lx + rpb - 1) / rpb;
-    k_partial_sums<<<dim3(nblk, B), kSumThreads, 0, st>>>(th, th_dn, pi, partial, Lx, L, nblk, rpb,
-                                                          plane ? plane : (size_t)Lx * L, dn_in_place);
-    count_launch();
-    U1_CHECK_LAUNCH();
+    const size_t pl = plane ? plane : (size_t)Lx * L;
+    for (int b0 = 0; b0 < B; b0 += kMaxGridY) {            // chains ride in gridDim.y (<= 65535 per launch)
+        const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+        k_partial_sums<<<dim3(nblk, nb), kSumThreads, 0, st>>>(th + (size_t)b0 * 2 * pl, th_dn, pi ? pi + (size_t)b0 * 2 * pl : nullptr,
+                                                               partial + (size_t)b0 * nblk * 3, Lx, L, nblk, rpb, pl, dn_in_place);
+        count_launch();
+        U1_CHECK_LAUNCH();
+    }
     k_finish_sums<<<B, 128, 0, st>>>(partial, sums, nblk);
     count_launch();
     U1_CHECK_LAUNCH();
@@ -927,13 +953,15 @@ static int launch_resident_pf(const TrajArgs& a, cudaStream_t st) {
     }
     int grid = a.B;
     if (PF) {                                         // persistent: as many CTAs as can be resident at once
-        static int slots = 0;
+        static std::atomic<int> slots_of[kMaxDevices];        // per device, race-free (same value from any thread)
+        const int dev = current_device();
+        int slots = slots_of[dev].load(std::memory_order_acquire);
         if (slots == 0) {
-            int dev = 0, sms = 0, occ = 0;
-            cudaGetDevice(&dev);
+            int sms = 0, occ = 0;
             if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traj_resident<L, TX, TY, PF>, NTX * NTY, smem) != cudaSuccess || occ < 1) occ = 1;
             slots = sms * occ;
+            slots_of[dev].store(slots, std::memory_order_release);
         }
         if (grid > slots) grid = slots;
     }
@@ -1155,6 +1183,7 @@ int u1_leapfrog_step(const double* theta_in, const double* pi_in, double* theta_
     g_launches = 0;
     if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(theta_out) || !aligned16(pi_out)) return U1_ERR_ARG;
     StepArgs a{};
     a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
     a.Lx = L; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
@@ -1167,6 +1196,7 @@ int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* t
     g_launches = 0;
     if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || Lx <= 0) return U1_ERR_ARG;
     if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(theta_out) || !aligned16(pi_out)) return U1_ERR_ARG;
     StepArgs a{};
     a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
     a.Lx = Lx; a.L = L; a.beta = beta; a.drift = drift; a.kick = kick;
@@ -1179,6 +1209,7 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
     g_launches = 0;
     if (!thetaA || !piA || !thetaB || !piB || !result_in_B || B <= 0 || L <= 0 || Lx <= 0 || n < 0) return U1_ERR_ARG;
     if (thetaA == thetaB || piA == piB) return U1_ERR_ARG;
+    if (!aligned16(thetaA) || !aligned16(piA) || !aligned16(thetaB) || !aligned16(piB)) return U1_ERR_ARG;
     const double *ct = thetaA, *cp = piA;
     if (n > 0)
         U1_TRY(leapfrog_steps(thetaA, piA, thetaA, piA, thetaB, piB, B, Lx, L, beta, first_drift, dt, n,
@@ -1215,6 +1246,7 @@ int u1_leapfrog(const double* theta_in, const double* pi_in, double* theta_out, 
     g_launches = 0;
     if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
+    if (!aligned16(theta_in) || !aligned16(pi_in)) return U1_ERR_ARG;
     U1_TRY(check_ws(ws, ws_bytes, u1_workspace_bytes(B, L)));
     PlainWs w = carve_plain(ws, B, L);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1239,6 +1271,9 @@ int u1_trajectory(double* theta, const double* pi_inject, const double* u_inject
     g_launches = 0;
     if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
+    // both kernel paths move fields as double2 / TMA bulk copies: 16-byte aligned chain bases are required
+    // (L even makes every chain base aligned once the first one is)
+    if (!aligned16(theta) || (pi_inject && !aligned16(pi_inject))) return U1_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool resident = (path == 2) || (path == 0 && resident_supported(L));
     if (resident) {
@@ -1298,6 +1333,7 @@ int u1_slab_leapfrog_step(const double* theta_in, const double* pi_in,
         Lx <= 0 || L <= 0)
         return U1_ERR_ARG;
     if (theta_in == theta_out || pi_in == pi_out) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(theta_out) || !aligned16(pi_out)) return U1_ERR_ARG;
     StepArgs a{};
     a.th = theta_in; a.pi = pi_in; a.tho = theta_out; a.pio = pi_out;
     a.th_up = theta_up; a.pi_up = pi_up; a.th_dn = theta_dn; a.pi_dn = pi_dn;

@@ -27,6 +27,9 @@ class FieldTransformation:
         self.L = int(lattice_size)
         self.device = torch.device(device)
         self.n_subsets = n_subsets
+        if if_check_jac and lattice_size > 16:
+            raise ValueError("if_check_jac builds the dense (2 L^2)^2 Jacobian: supported for lattice_size <= 16 "
+                             "(the reference's autograd version, field_trans_opt.py:385-390, is only feasible there too)")
         self.if_check_jac = if_check_jac
         self.num_workers = num_workers
         self.train_beta = None
@@ -53,8 +56,9 @@ class FieldTransformation:
         n_res = self.models[0].n_res_blocks
         assert blob.numel() == self._lib.u1ft_weight_count(n_res)
         h = C.c_void_p()
-        _lib.check(self._lib.u1ft_create(C.byref(h), n_res, blob.data_ptr(), blob.numel()), "u1ft_create")
-        self._release()
+        with torch.cuda.device(self._dev):       # the handle's device table must live on the compute device
+            _lib.check(self._lib.u1ft_create(C.byref(h), n_res, blob.data_ptr(), blob.numel()), "u1ft_create")
+            self._release()
         self._handle = h
 
     def _release(self):
@@ -269,12 +273,41 @@ class FieldTransformation:
         self._count()
         return self._back(out, theta, single)
 
+    def compute_jac_logdet_autograd(self, theta, eps: float = 1e-5):
+        """field_trans_opt.py:385-390 (verification path of if_check_jac): log|det dF/dtheta| of the FIRST
+        configuration from the dense Jacobian.  The reference gets the Jacobian from torch.autograd; here it
+        comes from central differences of the CUDA forward map (all 2n perturbed configurations in one
+        launch, n = 2 L^2; relative error ~eps^2), the determinant from torch.linalg.slogdet on the host.
+        Returns a 1-element tensor like the reference."""
+        d, single, B = self._stage(theta)
+        n = 2 * self.L * self.L
+        if self.L > 16:
+            raise ValueError("dense Jacobian check supported for lattice_size <= 16")
+        base = d[0].reshape(1, n)
+        eye = torch.eye(n, dtype=torch.float64, device=self._dev) * eps
+        pert = torch.cat([base + eye, base - eye], dim=0).reshape(2 * n, 2, self.L, self.L)
+        out = self.forward(pert).reshape(2, n, n)
+        jac = ((out[0] - out[1]) / (2 * eps)).T.contiguous()        # jac[i][j] = d out_i / d theta_j
+        sign, ld = torch.linalg.slogdet(jac.cpu())
+        return (ld if sign > 0 else ld * float("nan")).reshape(1).to(self._dev)
+
     # ------------------------------------------------------------------ training loss, forward value
     def compute_force(self, theta, beta, transformed: bool = False):
         """field_trans_opt.py:400-441: force of -beta sum cos P (plain, u1_force) or of S_FT (u1ft_force).
-        Values only: the reference's create_graph=True (needed to differentiate the loss with respect to the
-        CNN weights) is the training path and stays out of scope."""
+        With if_check_jac the analytic log-det of the first configuration is compared with the dense-Jacobian
+        one and the reference's message is printed (field_trans_opt.py:420-430)."""
         if transformed:
+            if self.if_check_jac:
+                ld = self.compute_jac_logdet(theta if theta.dim() == 4 else theta[None])
+                ld_dense = self.compute_jac_logdet_autograd(theta)
+                diff = (ld_dense[0] - ld[0]) / ld[0]
+                if abs(diff.item()) > 1e-4:
+                    self.print(f"\nWarning: Jacobian log determinant difference = {diff:.2f}")
+                    self.print(">>> Jacobian is not correct!")
+                else:
+                    self.print(f"\nJacobian log det (manual): {ld[0]:.2e}, (autograd): {ld_dense[0]:.2e}")
+                    self.print(">>> Jacobian is all good!")
+                self.last_jac_check = float(diff.item())
             return self.new_force(theta, beta)
         d, single, B = self._stage(theta)
         out = torch.empty_like(d)

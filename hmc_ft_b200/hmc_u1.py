@@ -17,7 +17,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev
+from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev, tune_search
 
 try:                                    # progress bars are cosmetic
     from tqdm import tqdm
@@ -114,23 +114,29 @@ class HMC_U1:
                                              stream_ptr(self._dev)), "u1_leapfrog")
         return self._back(to, theta, single), self._back(po, theta, single)
 
-    def trajectories(self, theta_dev: torch.Tensor, n_traj: int = 1, pi=None, u=None, want_obs: bool = True):
+    def trajectories(self, theta_dev: torch.Tensor, n_traj: int = 1, pi=None, u=None, want_obs: bool = True,
+                     _seed=None, _chain0=None, _traj0=None, _advance: bool = True):
         """n_traj Metropolis steps on the device-resident batch `theta_dev` ([B,2,L,L] fp64, updated
-        IN PLACE).  Returns dict of device tensors [n_traj,B]: dH, accept, H, plaq, topo."""
+        IN PLACE).  Returns dict of device tensors [n_traj,B]: dH, accept, H, plaq, topo.
+        (_seed/_chain0/_traj0/_advance: Philox stream override used by tune_step_size.)"""
         B, L = check_field(theta_dev)
         dev = self._dev
+        seed = self.seed if _seed is None else int(_seed)
+        chain0 = self.chain_offset if _chain0 is None else int(_chain0)
+        traj0 = self.traj_counter if _traj0 is None else int(_traj0)
         out = {k: torch.empty((n_traj, B), dtype=torch.float64, device=dev) for k in ("dH", "H", "plaq", "topo")}
         out["accept"] = torch.empty((n_traj, B), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             ws, nb = self._ws(B)
             _lib.check(self._lib.u1_trajectory(
-                theta_dev.data_ptr(), ptr(pi), ptr(u), self.seed, self.chain_offset, self.traj_counter, n_traj,
+                theta_dev.data_ptr(), ptr(pi), ptr(u), seed, chain0, traj0, n_traj,
                 B, L, self.beta, self.dt, self.n_steps,
                 out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
                 out["plaq"].data_ptr() if want_obs else None, out["topo"].data_ptr() if want_obs else None,
                 self.kernel_path, ws, nb, stream_ptr(dev)), "u1_trajectory")
         self.gpu_launches += _lib.last_launch_count()
-        self.traj_counter += n_traj
+        if _advance:
+            self.traj_counter += n_traj
         return out
 
     def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices=8):
@@ -139,7 +145,9 @@ class HMC_U1:
         whose H2D copy, trajectory kernel and D2H copy run on rotating CUDA
         streams, so the two PCIe directions and the SMs overlap.  Returns (theta_out_host, obs_host)
         with obs_host = pinned fp64 [4,B] = (accept, H, plaq, topo).  Chains keep their global Philox
-        ids (chain_offset + index), so the result equals the resident path bit for bit."""
+        ids (chain_offset + index), so the result equals the resident path bit for bit.
+        The D2H copies are ASYNCHRONOUS on the current stream: synchronize it (or the device) before the
+        host reads `theta_out_host` / `obs_host`."""
         if theta_host.device.type != "cpu" or theta_host.dim() != 4 or theta_host.dtype != torch.float64:
             raise ValueError("step_host expects a CPU fp64 tensor [B,2,L,L]")
         B, L = check_field(theta_host)
@@ -213,38 +221,16 @@ class HMC_U1:
         return self._back(d, theta), self._back(r["accept"][0].bool(), theta), self._back(r["H"][0], theta)
 
     def tune_step_size(self, n_tune_steps=2000, target_rate=0.65, target_tolerance=0.15,
-                       initial_step_size=0.2, max_attempts=10, theta=None):
+                       initial_step_size=0.2, max_attempts=10, theta=None, draws=None):
         """hmc_u1.py:99-161: binary search on dt.  As in the reference, every trial trajectory
-        starts from the same `theta` (the returned state is discarded, hmc_u1.py:132).  With a
-        batch of chains the acceptance rate is the mean over chains."""
+        starts from the same `theta` (the returned state is discarded, hmc_u1.py:132), so the trials of
+        one attempt are independent and run as extra chains of ONE launch (_runtime.tune_search).  With a
+        batch of chains the acceptance rate is the mean over chains.  draws=(pi, u) injects the draws in
+        the order the reference consumes them (parity test).  Returns the [(dt, rate)] history."""
         theta = self.initialize() if theta is None else theta
         base, _ = self._stage(theta)
-        self.dt = initial_step_size
-        step_min, step_max = 1e-6, 1.0
-        best_dt, best_diff = self.dt, float("inf")
-        rate = 0.0
-        for attempt in range(max_attempts):
-            acc = torch.zeros((), dtype=torch.float64, device=self._dev)
-            for _ in range(n_tune_steps):
-                r = self.trajectories(base.clone(), 1, want_obs=False)
-                acc += r["accept"].double().mean()
-            rate = (acc / n_tune_steps).item()
-            diff = abs(rate - target_rate)
-            self._print(f"Step size: {self.dt:.6f}, Acceptance rate: {rate:.2%}")
-            if diff < best_diff:
-                best_dt, best_diff = self.dt, diff
-            if diff <= target_tolerance:
-                self._print(f"Found good step size: {self.dt:.6f}")
-                break
-            if rate > target_rate:
-                step_min = self.dt
-                self.dt = min((self.dt + step_max) / 2, step_max)
-            else:
-                step_max = self.dt
-                self.dt = max((self.dt + step_min) / 2, step_min)
-        if abs(rate - target_rate) > target_tolerance:
-            self._print(f"Using best found step size: {best_dt:.6f}")
-            self.dt = best_dt
+        return tune_search(self, base, n_tune_steps, target_rate, target_tolerance, initial_step_size,
+                           max_attempts, draws)
 
     def thermalize(self):
         """hmc_u1.py:163-196: rough thermalisation, optional tuning, restart from cold, then

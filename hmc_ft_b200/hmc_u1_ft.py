@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev
+from ._runtime import WS, as_batch, check_field, ptr, require_cuda, stream_ptr, to_dev, tune_search
 from .field_trans import FieldTransformation
 from .hmc_u1 import HMC_U1
 from .utils import plaq_mean_from_field, regularize
@@ -63,6 +63,9 @@ class HMC_U1_FT:
         self.ft = _resolve_ft(field_transformation, compute_jac_logdet, self.lattice_size)
         if self.ft is not None and self.ft.L != self.lattice_size:
             raise ValueError("FieldTransformation lattice size differs from HMC_U1_FT lattice size")
+        if self.ft is not None and self.ft._dev != self._dev:
+            raise ValueError(f"FieldTransformation lives on {self.ft._dev}, HMC_U1_FT on {self._dev}: "
+                             "the weight handle, the workspace and theta must share one device")
         self._plain = None
         if self.ft is None:     # identity transformation: the plain kernels are the exact same chain
             self._plain = HMC_U1(lattice_size, beta, n_thermalization_steps, n_steps, step_size, device=device,
@@ -129,32 +132,39 @@ class HMC_U1_FT:
         self.gpu_launches += _lib.last_launch_count()
         return self._back(to, theta, single), self._back(po, theta, single)
 
-    def trajectories(self, theta_dev, n_traj=1, pi=None, u=None, want_ori=False):
+    def trajectories(self, theta_dev, n_traj=1, pi=None, u=None, want_ori=False,
+                     _seed=None, _chain0=None, _traj0=None, _advance: bool = True):
         """n_traj FT-HMC Metropolis steps on the device batch theta_dev (in place).  Returns dict of
         device tensors [n_traj,B]: dH, accept, H, plaq, topo (observables of F(theta), as
         hmc_u1_ft.py:348-358) and optionally theta_ori [B,2,L,L] of the final state."""
         if self.ft is None:
             self._plain.dt, self._plain.traj_counter = self.dt, self.traj_counter
-            r = self._plain.trajectories(theta_dev, n_traj, pi, u)
-            self.traj_counter += n_traj
+            r = self._plain.trajectories(theta_dev, n_traj, pi, u, _seed=_seed, _chain0=_chain0, _traj0=_traj0,
+                                         _advance=_advance)
+            if _advance:
+                self.traj_counter += n_traj
             self.gpu_launches = self._plain.gpu_launches
             if want_ori:
                 r["theta_ori"] = theta_dev.clone()
             return r
         B, L = check_field(theta_dev)
         dev = self._dev
+        seed = self.seed if _seed is None else int(_seed)
+        chain0 = self.chain_offset if _chain0 is None else int(_chain0)
+        traj0 = self.traj_counter if _traj0 is None else int(_traj0)
         out = {k: torch.empty((n_traj, B), dtype=torch.float64, device=dev) for k in ("dH", "H", "plaq", "topo")}
         out["accept"] = torch.empty((n_traj, B), dtype=torch.int32, device=dev)
         ori = torch.empty_like(theta_dev) if want_ori else None
         with torch.cuda.device(dev):
             ws, nb = self.ft.workspace(B, True)
             _lib.check(self._lib.u1ft_trajectory(
-                self.ft._handle, theta_dev.data_ptr(), ptr(pi), ptr(u), self.seed, self.chain_offset,
-                self.traj_counter, n_traj, B, L, self.beta, self.dt, self.n_steps,
+                self.ft._handle, theta_dev.data_ptr(), ptr(pi), ptr(u), seed, chain0,
+                traj0, n_traj, B, L, self.beta, self.dt, self.n_steps,
                 out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(), out["plaq"].data_ptr(),
                 out["topo"].data_ptr(), ptr(ori), ws, nb, stream_ptr(dev)), "u1ft_trajectory")
         self.gpu_launches += _lib.last_launch_count()
-        self.traj_counter += n_traj
+        if _advance:
+            self.traj_counter += n_traj
         if want_ori:
             out["theta_ori"] = ori
         return out
@@ -173,32 +183,13 @@ class HMC_U1_FT:
         return self._back(d, theta), self._back(r["accept"][0].bool(), theta), self._back(r["H"][0], theta)
 
     def tune_step_size(self, n_tune_steps=1000, target_rate=0.65, target_tolerance=0.15,
-                       initial_step_size=0.2, max_attempts=10, theta=None):
-        """hmc_u1_ft.py:211-273 (every trial starts from the same theta, as in the reference)."""
+                       initial_step_size=0.2, max_attempts=10, theta=None, draws=None):
+        """hmc_u1_ft.py:211-273: binary search on dt; every trial starts from the same theta (as in the
+        reference), so one attempt's trials run as extra chains of one launch (_runtime.tune_search)."""
         theta = self.initialize() if theta is None else theta
         base, _ = self._stage(theta)
-        self.dt = initial_step_size
-        step_min, step_max = 1e-6, 1.0
-        best_dt, best_diff, rate = self.dt, float("inf"), 0.0
-        for attempt in range(max_attempts):
-            acc = torch.zeros((), dtype=torch.float64, device=self._dev)
-            for _ in range(n_tune_steps):
-                acc += self.trajectories(base.clone(), 1)["accept"].double().mean()
-            rate = (acc / n_tune_steps).item()
-            diff = abs(rate - target_rate)
-            self._print(f"Step size: {self.dt:.6f}, Acceptance rate: {rate:.2%}")
-            if diff < best_diff:
-                best_dt, best_diff = self.dt, diff
-            if diff <= target_tolerance:
-                break
-            if rate > target_rate:
-                step_min = self.dt
-                self.dt = min((self.dt + step_max) / 2, step_max)
-            else:
-                step_max = self.dt
-                self.dt = max((self.dt + step_min) / 2, step_min)
-        if abs(rate - target_rate) > target_tolerance:
-            self.dt = best_dt
+        return tune_search(self, base, n_tune_steps, target_rate, target_tolerance, initial_step_size,
+                           max_attempts, draws)
 
     def thermalize(self):
         """hmc_u1_ft.py:275-316: plaquette of F(theta) recorded BEFORE each step."""

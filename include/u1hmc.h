@@ -12,8 +12,15 @@
  *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and
  *    allocation-free: scratch comes in through (ws, ws_bytes); query with *_workspace_bytes().
  *  - Return value: 0 ok, <0 argument error (U1_ERR_*), >0 a cudaError_t.  Nothing throws.
- *  - No global/constant-memory state.  FT weights live in an opaque per-handle host object and
- *    travel to the kernels as launch parameters.
+ *  - No device-global / constant-memory state: FT weights live in an opaque per-handle host object and
+ *    travel to the kernels as launch parameters; the handle's device table belongs to the device that was
+ *    current at u1ft_create and every u1ft_* call must run on that device (U1_ERR_HANDLE otherwise).
+ *    Host-side process state is limited to (a) tuning switches read once from the environment (U1_*,
+ *    U1FT_*) plus u1ft_set_chunk_sites, and (b) per-DEVICE caches of occupancy / function attributes,
+ *    indexed by the current device and updated atomically, so one process may drive several GPUs from
+ *    several threads.
+ *  - Field pointers must be 16-byte aligned (the kernels move double2 / TMA bulk copies): U1_ERR_ARG
+ *    otherwise.  Batches of any size are accepted (launches are sliced at 65535 chains internally).
  */
 #ifndef U1HMC_H
 #define U1HMC_H

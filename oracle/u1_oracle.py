@@ -410,6 +410,42 @@ class PlainHMCOracle:
         return metropolis_step(theta, pi, u, self.dt, self.n_steps, self.action, self.force)
 
 
+def tune_step_size(hmc, theta, pi_draws, u_draws, n_tune_steps=2000, target_rate=0.65, target_tolerance=0.15,
+                   initial_step_size=0.2, max_attempts=10):
+    """Binary search on dt, hmc_u1.py:99-161 (same for hmc_u1_ft.py:211-271), with the draws injected:
+    trial i of the whole search (attempt * n_tune_steps + step) consumes pi_draws[i], u_draws[i] - the
+    order in which the reference's metropolis_step pulls randn_like / rand from torch's generator.
+    Every trial starts from the same theta (the returned state is discarded, hmc_u1.py:132).
+    `hmc` is a PlainHMCOracle / FTHMCOracle; its dt is updated like the reference's self.dt.
+    Returns the history [(dt tried, acceptance rate)]; the tuned value is hmc.dt."""
+    hmc.dt = initial_step_size
+    step_min, step_max = 1e-6, 1.0
+    best_dt, best_diff = hmc.dt, float("inf")
+    history, i, rate = [], 0, 0.0
+    for _attempt in range(max_attempts):
+        count = 0
+        for _ in range(n_tune_steps):
+            _, acc, _, _ = hmc.metropolis_step(theta, pi_draws[i], u_draws[i])
+            count += int(bool(torch.as_tensor(acc).reshape(-1)[0]))
+            i += 1
+        rate = count / n_tune_steps
+        diff = abs(rate - target_rate)
+        history.append((hmc.dt, rate))
+        if diff < best_diff:
+            best_dt, best_diff = hmc.dt, diff
+        if abs(rate - target_rate) <= target_tolerance:
+            break
+        if rate > target_rate:
+            step_min = hmc.dt
+            hmc.dt = min((hmc.dt + step_max) / 2, step_max)
+        else:
+            step_max = hmc.dt
+            hmc.dt = max((hmc.dt + step_min) / 2, step_min)
+    if abs(rate - target_rate) > target_tolerance:
+        hmc.dt = best_dt
+    return history
+
+
 class FTHMCOracle:
     """HMC_U1_FT (hmc_u1_ft.py) with injected randomness, batched over chains."""
 
@@ -457,7 +493,7 @@ def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
 
 
 def u01_from_bits(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
-    """53-bit uniform in (0,1): ((hi<<21 | lo>>11) + 0.5) * 2^-53 — matches csrc/philox.cuh."""
+    """53-bit uniform in (0,1): ((hi<<21 | lo>>11) + 0.5) * 2^-53 — matches csrc/u1_common.cuh."""
     m = (hi.astype(np.uint64) << np.uint64(21)) | (lo.astype(np.uint64) >> np.uint64(11))
     return (m.astype(np.float64) + 0.5) * (2.0 ** -53)
 
@@ -465,7 +501,7 @@ def u01_from_bits(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
 def philox_momenta(seed: int, chain: int, traj: int, L: int) -> np.ndarray:
     """Momentum field pi[2,L,L] for (seed, global chain id, trajectory index), as the
     CUDA path generates it: one Philox call per site s=x*L+y with counter
-    (s, traj_lo, traj_hi, 0) and key (seed_lo ^ chain-mixed, ...) — see csrc/philox.cuh.
+    (s, traj_lo, traj_hi, 0) and key (seed_lo ^ chain-mixed, ...) — see csrc/u1_common.cuh.
     Box-Muller on two 53-bit uniforms gives (pi0, pi1) of that site."""
     s = np.arange(L * L, dtype=np.uint32)
     ctr = np.stack([s, np.full_like(s, traj & 0xFFFFFFFF), np.full_like(s, (traj >> 32) & 0xFFFFFFFF),

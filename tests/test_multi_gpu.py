@@ -25,3 +25,23 @@ def test_slab_multi_gpu_matches_plain_chain(world):
                           "--master-addr", "127.0.0.1", "--master-port", "29631", WORKER, "256", "4"],
                          capture_output=True, text=True, timeout=900)
     assert "SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+FT_WORKER = os.path.join(ROOT, "tests", "ft_shard_worker.py")
+
+
+def test_ft_chain_sharding_world1_observables():
+    out = subprocess.run([sys.executable, FT_WORKER], capture_output=True, text=True, timeout=900)
+    assert "FTSHARD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ft_chain_sharding_multi_gpu_observables(world):
+    """C4 'with topological charge and autocorrelation observables' across ranks: gathered Q histories and
+    Gamma(delta) equal the unsharded run bit for bit (Philox keyed by global chain id)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29641", FT_WORKER],
+                         capture_output=True, text=True, timeout=900)
+    assert "FTSHARD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

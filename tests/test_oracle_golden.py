@@ -168,3 +168,31 @@ def test_training_loss_value_matches_reference(golden_dir, tag, wfile):
     assert rel(ft.compute_force(th_new, float(z["train_beta"]), transformed=True), z["force_new"]) < 1e-12
     loss = ft.loss_fn(T(z["theta_ori"]), float(z["train_beta"]))
     assert abs(loss.item() - float(z["loss"])) < 1e-11 * abs(float(z["loss"]))
+
+
+@pytest.mark.parametrize("L", [6, 8, 16])
+def test_rectangles_match_reference(golden_dir, L):
+    """utils.py:118-141 rect_from_field_batch / plaq_from_field_batch, reference outputs (tools/gen_golden_rect_tune.py)."""
+    z = np.load(os.path.join(golden_dir, "rect.npz"))
+    th = T(z[f"theta_L{L}"])
+    assert rel(O.rect_from_field(th), z[f"rect_L{L}"]) == 0.0
+    assert rel(O.plaq_from_field(th), z[f"plaq_L{L}"]) == 0.0
+    # R0(x,y) = P(x,y) + P(x+1,y), R1(x,y) = P(x,y) + P(x,y+1): the identity the FT reverse pass relies on
+    P = O.plaq_from_field(th)
+    r = O.rect_from_field(th)
+    assert rel(P + torch.roll(P, -1, -2), r[:, 0]) < 1e-14 and rel(P + torch.roll(P, -1, -1), r[:, 1]) < 1e-14
+
+
+def test_tune_step_size_matches_reference(golden_dir):
+    """hmc_u1.py:99-161: the oracle's binary search replays the REAL reference's search (history of (dt, rate)
+    and the tuned dt) when fed the draws the reference consumed from torch's generator."""
+    z = np.load(os.path.join(golden_dir, "tune.npz"))
+    L, beta, n_steps, n_tune, target, tol, dt0, max_att = z["params"]
+    h = O.PlainHMCOracle(int(L), float(beta), int(n_steps), float(dt0))
+    hist = O.tune_step_size(h, T(z["theta"])[None], T(z["pi"])[:, None], T(z["u"])[:, None], int(n_tune), float(target),
+                            float(tol), float(dt0), int(max_att))
+    assert len(hist) == len(z["hist_dt"])
+    for (dt, rate), dt_ref, rate_ref in zip(hist, z["hist_dt"], z["hist_rate"]):
+        assert abs(dt - dt_ref) < 1e-6                       # the reference prints 6 decimals
+        assert round(rate * int(n_tune)) == round(float(rate_ref) * int(n_tune))
+    assert h.dt == float(z["tuned_dt"])

@@ -335,3 +335,91 @@ def test_full_size_size_independent_properties(hb):
     q1 = hk.trajectories(x1, 1, pi=pa, u=u0)
     assert (q0["dH"] - q1["dH"]).abs().max().item() < 1e-8 and torch.equal(q0["accept"], q1["accept"])
     assert torch.equal(q0["topo"], q1["topo"]) and (q0["plaq"] - q1["plaq"]).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("L", [6, 8, 16])
+def test_rectangle_golden(hb, golden_dir, L):
+    """u1_rectangle / utils.rect_from_field_batch against the reference's rect_from_field_batch (utils.py:129-141)."""
+    from hmc_ft_b200 import utils as U
+    z = np.load(os.path.join(golden_dir, "rect.npz"))
+    th = torch.tensor(z[f"theta_L{L}"], dtype=torch.float64, device="cuda")
+    r = U.rect_from_field_batch(th)
+    assert r.shape == (3, 2, L, L) and rel(r, z[f"rect_L{L}"]) < 1e-15
+    assert rel(U.plaq_from_field_batch(th), z[f"plaq_L{L}"]) < 1e-15
+    # single configuration and host-tensor call paths
+    assert rel(U.rect_from_field_batch(th[1:2])[0], z[f"rect_L{L}"][1]) < 1e-15
+    rh = U.rect_from_field_batch(torch.tensor(z[f"theta_L{L}"]))
+    assert rh.device.type == "cpu" and rel(rh, z[f"rect_L{L}"]) < 1e-15
+
+
+def test_tune_step_size_matches_reference_search(hb, golden_dir):
+    """HMC_U1.tune_step_size with the draws the REAL reference consumed (tests/golden/tune.npz): same (dt, rate)
+    history, same tuned dt (hmc_u1.py:99-161), and the same answer as the oracle's restatement."""
+    z = np.load(os.path.join(golden_dir, "tune.npz"))
+    L, beta, n_steps, n_tune, target, tol, dt0, max_att = z["params"]
+    L, n_steps, n_tune, max_att = int(L), int(n_steps), int(n_tune), int(max_att)
+    th = torch.tensor(z["theta"], dtype=torch.float64)
+    pi, u = torch.tensor(z["pi"]), torch.tensor(z["u"])
+    for path in (0, 1):
+        h = hb.HMC_U1(L, float(beta), 0, n_steps, float(dt0), device="cuda", if_tune_step_size=True, kernel_path=path)
+        c0 = h.traj_counter
+        hist = h.tune_step_size(n_tune, float(target), float(tol), float(dt0), max_att, theta=th.cuda(), draws=(pi, u))
+        assert len(hist) == len(z["hist_dt"])
+        for (dt, rate), dt_ref, rate_ref in zip(hist, z["hist_dt"], z["hist_rate"]):
+            assert abs(dt - dt_ref) < 1e-6
+            assert round(rate * n_tune) == round(float(rate_ref) * n_tune)
+        assert h.dt == float(z["tuned_dt"])
+        assert h.traj_counter == c0 + len(hist)
+    ho = O.PlainHMCOracle(L, float(beta), n_steps, float(dt0))
+    O.tune_step_size(ho, th[None], pi[:, None], u[:, None], n_tune, float(target), float(tol), float(dt0), max_att)
+    assert ho.dt == h.dt
+
+
+def test_tune_step_size_batched_philox(hb):
+    """Without injected draws: the batched search (all trials of an attempt in one launch, chunked when the
+    replicas exceed max_bytes) lands inside the tolerance band, is reproducible, and does not depend on the
+    chunking."""
+    from hmc_ft_b200._runtime import tune_search
+    L, beta = 16, 2.0
+    res = []
+    for max_bytes in (1 << 30, 5 * 4 * 2 * L * L * 8):            # second: 5 trials per launch
+        h = hb.HMC_U1(L, beta, 10, 10, 0.2, device="cuda", if_tune_step_size=True, n_chains=4, seed=11)
+        base = torch.zeros(4, 2, L, L, dtype=torch.float64, device="cuda")
+        h.trajectories(base, 10)
+        hist = tune_search(h, base, 64, 0.65, 0.1, 0.9, 10, None, max_bytes)
+        assert abs(hist[-1][1] - 0.65) <= 0.1 and h.dt == hist[-1][0]
+        res.append(hist)
+    assert res[0] == res[1]
+
+
+def test_misaligned_pointer_is_rejected(hb):
+    """include/u1hmc.h: field pointers must be 16-byte aligned (double2 / TMA bulk copies) -> U1_ERR_ARG, no fault."""
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    L, B = 8, 2
+    buf = torch.zeros(B * 2 * L * L + 2, dtype=torch.float64, device="cuda")
+    odd = buf[1:]                                   # 8-byte aligned only
+    assert odd.data_ptr() % 16 == 8
+    ws = torch.empty(lib.u1_workspace_bytes(B, L), dtype=torch.uint8, device="cuda")
+    for path in (0, 1, 2):
+        st = lib.u1_trajectory(odd.data_ptr(), None, None, 1, 0, 0, 1, B, L, 1.0, 0.1, 2, None, None, None, None, None,
+                               path, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        assert st == -1
+    torch.cuda.synchronize()
+
+
+def test_more_than_65535_chains(hb):
+    """Chains ride in gridDim.y of the streaming kernels: batches above 65535 are sliced internally."""
+    L, B = 6, 65535 + 300                       # L=6 has no resident kernel: streaming path
+    g = torch.Generator().manual_seed(3)
+    th = ((torch.rand(B, 2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * 3.0).cuda()
+    h = hb.HMC_U1(L, 2.0, 0, 4, 0.1, device="cuda", if_tune_step_size=False, n_chains=B, seed=5)
+    S = h.action(th)
+    So = O.action(th[-400:].cpu(), 2.0)
+    assert rel(S[-400:], So) < 1e-12
+    a = th.clone()
+    r = h.trajectories(a, 1)
+    h2 = hb.HMC_U1(L, 2.0, 0, 4, 0.1, device="cuda", if_tune_step_size=False, n_chains=400, seed=5, chain_offset=B - 400)
+    b = th[-400:].clone()
+    r2 = h2.trajectories(b, 1)
+    assert torch.equal(r["dH"][0, -400:], r2["dH"][0]) and torch.equal(a[-400:], b)
