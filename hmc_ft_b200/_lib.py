@@ -42,6 +42,19 @@ SIGNATURES = {
     "u1_select_accepted": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "u1_slab_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1_slab_sums_ext": (_i, [_vp, _vp, C.c_size_t, _vp, _i, _i, _vp, C.c_size_t, _vp]),
+    "u1_ipc_handle_bytes": (_sz, []),
+    "u1_slab_peer_region_bytes": (_sz, [_i, _i]),
+    "u1_peer_alloc": (_i, [C.POINTER(_vp), _sz, _vp]),
+    "u1_peer_open": (_i, [_vp, C.POINTER(_vp)]),
+    "u1_peer_close": (_i, [_vp]),
+    "u1_peer_free": (_i, [_vp]),
+    "u1_slab_peer_status": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
+    "u1_slab_exchange": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "u1_slab_metropolis_peer": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _d, _d, _i, _i, C.POINTER(_vp),
+                                     _vp, _vp, _vp, _vp, _vp, _vp]),
+    "u1_slab_drift_wrap": (_i, [_vp, _vp, _sz, _i, _i, _d, _vp]),
+    "u1_slab_copy_in": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "u1_slab_select": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
     "u1_diff_power_sums_workspace_bytes": (C.c_size_t, []),
     "u1_diff_power_sums": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp]),
     "u1ft_create": (_i, [C.POINTER(_vp), _i, _vp, _sz]),

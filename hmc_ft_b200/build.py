@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libu1hmc.so")
-SOURCES = ["u1_plain.cu", "u1_ft.cu"]
+SOURCES = ["u1_plain.cu", "u1_ft.cu", "u1_slab.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xptxas=-v",

@@ -169,6 +169,33 @@ class HMC_U1_FT:
             out["theta_ori"] = ori
         return out
 
+    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None):
+        """One FT-HMC Metropolis step of a HOST-resident batch [B,2,L,L] (fp64, ideally pinned): H2D copy,
+        u1ft_trajectory, D2H of the new configurations and of the per-chain (dH, accept, H, plaq, topo) as one
+        pinned [5,B] block.  The step is compute-bound (seconds of FP64 work against milliseconds of PCIe), so
+        unlike HMC_U1.step_host there is nothing to pipeline.  The D2H copies are ASYNCHRONOUS on the current
+        stream: synchronize before the host reads the results."""
+        if theta_host.device.type != "cpu" or theta_host.dim() != 4 or theta_host.dtype != torch.float64:
+            raise ValueError("step_host expects a CPU fp64 tensor [B,2,L,L]")
+        B, L = check_field(theta_host)
+        if not theta_host.is_pinned():
+            theta_host = theta_host.pin_memory()
+        if out_host is None:
+            out_host = torch.empty_like(theta_host).pin_memory()
+        st = getattr(self, "_host_state", None)
+        if st is None or st["key"] != (B, L):
+            st = {"key": (B, L), "dev": torch.empty((B, 2, L, L), dtype=torch.float64, device=self._dev),
+                  "obs_d": torch.empty((5, B), dtype=torch.float64, device=self._dev),
+                  "obs_h": torch.empty((5, B), dtype=torch.float64).pin_memory()}
+            self._host_state = st
+        st["dev"].copy_(theta_host, non_blocking=True)
+        r = self.trajectories(st["dev"], 1)
+        o = st["obs_d"]
+        o[0].copy_(r["dH"][0]); o[1].copy_(r["accept"][0]); o[2].copy_(r["H"][0]); o[3].copy_(r["plaq"][0]); o[4].copy_(r["topo"][0])
+        out_host.copy_(st["dev"], non_blocking=True)
+        st["obs_h"].copy_(o, non_blocking=True)
+        return out_host, st["obs_h"]
+
     def metropolis_step(self, theta, pi=None, u=None):
         """hmc_u1_ft.py:181-209."""
         d, single = self._stage(theta)

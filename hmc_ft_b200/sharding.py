@@ -5,9 +5,13 @@
      same for any GPU count; only per-chain observables are gathered.
 (ii) Domain decomposition of one large lattice (configs[4], L=4096): 1-D slabs along x.  Each rank
      keeps an extended slab (own rows + k halo rows per side).  Halos of (theta, pi) are exchanged
-     with the two ring neighbours once every k leapfrog steps (NCCL send/recv over NVLink); between
-     exchanges the extended slab is advanced as a whole and the outer rows, which become stale one
-     row per step, are simply never used.  dH needs one 3-double all-reduce per Hamiltonian.
+     with the two ring neighbours once every k leapfrog steps; between exchanges the extended slab is
+     advanced as a whole and the outer rows, which become stale one row per step, are simply never
+     used.  Transport "peer" (default on GPUs): our own kernels store the edge rows straight into the
+     neighbours' memory over NVLink and synchronise through epoch flags (csrc/u1_slab.cu), the
+     Hamiltonian sums are all-gathered the same way, so a trajectory contains no NCCL call and is
+     replayed as ONE CUDA graph per rank.  Transport "nccl": send/recv + all-reduce through
+     torch.distributed (fallback; also what the gloo CPU tests exercise).
      The reference has no such path; results are checked against the undecomposed chain.
 """
 from __future__ import annotations
@@ -91,24 +95,140 @@ class HaloExchanger:
         self.bytes_sent += (s_up.numel() + s_dn.numel()) * s_up.element_size()
 
 
+# ----------------------------------------------------------------------------- NVLink peer regions
+class PeerRegions:
+    """Table of the peer-region device pointers of all ranks of one slab decomposition (csrc/u1_slab.cu).
+
+    PeerRegions.ipc(k, L, group): one process per GPU - every rank allocates its region with u1_peer_alloc,
+    the CUDA IPC handles are all-gathered through torch.distributed (plumbing only) and opened with
+    u1_peer_open; afterwards the data path never touches torch.distributed again.
+    PeerRegions.local(world, k, L): `world` regions in THIS process on the current device (virtual ranks on
+    one GPU for tests, and the degenerate world == 1 case)."""
+
+    def __init__(self, lib, rank: int, world: int, ptrs, owned, opened):
+        self._lib, self.rank, self.world = lib, rank, world
+        self.ptrs = list(ptrs)                        # device pointers, index = rank
+        self._owned, self._opened = list(owned), list(opened)
+        self.table = (C.c_void_p * world)(*[C.c_void_p(p) for p in self.ptrs])
+
+    @classmethod
+    def local(cls, world: int, k: int, L: int, device=None):
+        lib = _lib.load()
+        dev = require_cuda(device)
+        nbytes = lib.u1_slab_peer_region_bytes(int(k), int(L))
+        ptrs = []
+        with torch.cuda.device(dev):
+            for _ in range(world):
+                p = C.c_void_p()
+                _lib.check(lib.u1_peer_alloc(C.byref(p), nbytes, None), "u1_peer_alloc")
+                ptrs.append(p.value)
+        shared = {"refs": world, "ptrs": ptrs}
+        out = []
+        for r in range(world):
+            pr = cls(lib, r, world, ptrs, [], [])
+            pr._shared = shared
+            out.append(pr)
+        return out
+
+    @classmethod
+    def ipc(cls, k: int, L: int, group=None, device=None):
+        lib = _lib.load()
+        dev = require_cuda(device)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = lib.u1_slab_peer_region_bytes(int(k), int(L))
+        hb = lib.u1_ipc_handle_bytes()
+        handle = (C.c_ubyte * hb)()
+        mine = C.c_void_p()
+        err = None
+        with torch.cuda.device(dev):
+            st = lib.u1_peer_alloc(C.byref(mine), nbytes, handle)
+            if st != 0:
+                err = f"u1_peer_alloc: status {st} ({lib.u1_status_string(st).decode()})"
+            handles = [None] * world
+            dist.all_gather_object(handles, None if err else bytes(handle), group=group)
+            ptrs, opened = [], []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(mine.value)
+                    continue
+                if err or handles[r] is None:
+                    err = err or f"rank {r} could not export its peer region"
+                    ptrs.append(None)
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * hb).from_buffer_copy(handles[r])
+                st = lib.u1_peer_open(buf, C.byref(p))
+                if st != 0:
+                    err = f"u1_peer_open (CUDA IPC) of rank {r}: status {st} ({lib.u1_status_string(st).decode()})"
+                    ptrs.append(None)
+                    continue
+                ptrs.append(p.value)
+                opened.append(p.value)
+            # every rank learns whether ALL ranks succeeded, so a failure raises everywhere instead of hanging some
+            errs = [None] * world
+            dist.all_gather_object(errs, err, group=group)
+        if any(errs):
+            for p in opened:
+                lib.u1_peer_close(p)
+            if mine.value:
+                lib.u1_peer_free(mine.value)
+            raise _lib.U1Error("NVLink peer regions unavailable: " + "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
+        return cls(lib, rank, world, ptrs, [mine.value], opened)
+
+    def status(self):
+        """Control words of the own region (host sync): dict with the exchange / Metropolis epochs and `error`."""
+        w = (C.c_ulonglong * 8)()
+        _lib.check(self._lib.u1_slab_peer_status(self.ptrs[self.rank], w), "u1_slab_peer_status")
+        return {"exchange_epoch": int(w[2]), "metropolis_epoch": int(w[5]), "error": int(w[6])}
+
+    def close(self):
+        for p in self._opened:
+            self._lib.u1_peer_close(p)
+        for p in self._owned:
+            self._lib.u1_peer_free(p)
+        self._opened, self._owned = [], []
+        sh = getattr(self, "_shared", None)
+        if sh is not None:
+            sh["refs"] -= 1
+            if sh["refs"] == 0:
+                for p in sh["ptrs"]:
+                    self._lib.u1_peer_free(p)
+            self._shared = None
+
+
 # ----------------------------------------------------------------------------- slab HMC
 class SlabHMC:
     """Plain HMC (hmc_u1.py:82-97 semantics) of ONE L x L lattice decomposed into `world` slabs of
     Lx = L/world rows.  Momenta are keyed by the global site index and the accept draw by
-    (seed, chain, traj) only, so every rank takes the same Metropolis decision and the chain is
-    identical (up to reduction round-off in dH) to the undecomposed one."""
+    (seed, chain, traj) only, and every rank adds the Hamiltonian sums of all ranks in the same order,
+    so every rank takes the same Metropolis decision and the chain is identical (up to reduction
+    round-off in dH) to the undecomposed one.
+
+    transport: "peer" (NVLink peer-memory kernels, whole trajectory in one CUDA graph; default on CUDA),
+    "nccl" (torch.distributed send/recv + all-reduce).  `peers` / `rank` / `world` let a test run several
+    virtual ranks inside one process (PeerRegions.local)."""
 
     def __init__(self, lattice_size: int, beta: float, n_steps: int, step_size: float, halo: Optional[int] = None,
-                 seed: int = 1331, chain: int = 0, group=None, device=None):
+                 seed: int = 1331, chain: int = 0, group=None, device=None, transport: Optional[str] = None,
+                 peers: Optional[PeerRegions] = None, rank: Optional[int] = None, world: Optional[int] = None):
         self.L, self.beta, self.n_steps, self.dt = int(lattice_size), float(beta), int(n_steps), float(step_size)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if peers is not None:
+            self.world, self.rank = peers.world, peers.rank
+        else:
+            self.world = int(world) if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+            self.rank = int(rank) if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         if self.L % self.world or self.L % 2:
             raise ValueError("L must be even and divisible by the number of ranks")
         self.Lx = self.L // self.world
-        if halo is None:       # auto: trade redundant rows (2k/Lx extra compute) for fewer exchanges (one per k steps)
-            halo = max(10, self.Lx // 16)
+        self.transport = transport or os.environ.get("U1_SLAB_TRANSPORT", "peer")
+        if self.transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        if halo is None:
+            # peer: an exchange is one ~10-20 us kernel, so few redundant rows win (2k/Lx extra compute, one
+            # exchange per k steps); nccl: host-driven send/recv per exchange, so fewer, larger exchanges
+            env = os.environ.get("U1_SLAB_HALO")
+            halo = int(env) if env else (16 if self.transport == "peer" else max(10, self.Lx // 16))
         self.k = max(1, min(int(halo), self.Lx, self.n_steps))
         self.x0 = self.rank * self.Lx
         self.seed, self.chain = int(seed), int(chain)
@@ -117,19 +237,53 @@ class SlabHMC:
         self._lib = _lib.load()
         self._dev = require_cuda(device)
         self.halo = HaloExchanger(self.Lx, self.k, group)
+        self.halo.world, self.halo.rank = self.world, self.rank
+        self.halo.up, self.halo.dn = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         Lxe = self.Lx + 2 * self.k
         # ext[f][mu][row][y], f = 0 theta, 1 pi ; two buffers for the out-of-place step kernel
         self._ext = [torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev) for _ in range(2)]
         self._sums6 = torch.zeros(6, dtype=torch.float64, device=self._dev)     # [old sums | new sums]
-        # CUDA-graph replay of the trajectory: on by default for a single rank; with NCCL halo exchanges inside
-        # the capture (world > 1) it is opt-in (U1_SLAB_GRAPH=1) - a 2-GPU run with it hung in round 1.
-        self._graph_mode = os.environ.get("U1_SLAB_GRAPH", "1" if self.world == 1 else "0") == "1"
+        # private scratch for the sums kernels: a captured graph bakes this pointer in, so it must not be a
+        # shared grow-only cache entry
+        self._ws = torch.empty(4096 + 24 * (self.Lx + 2), dtype=torch.uint8, device=self._dev)
+        self.peers: Optional[PeerRegions] = None
+        self.peer_error: Optional[str] = None
+        if self.transport == "peer":
+            try:
+                if peers is not None:
+                    self.peers = peers
+                elif self.world == 1:
+                    self.peers = PeerRegions.local(1, self.k, self.L, self._dev)[0]
+                else:
+                    self.peers = PeerRegions.ipc(self.k, self.L, group, self._dev)
+            except _lib.U1Error as e:            # e.g. CUDA IPC not permitted in this container (raised on every rank)
+                self.peer_error = str(e)
+                raise
+        # CUDA-graph replay of the whole trajectory.  peer: on by default for any world size (no NCCL inside);
+        # nccl: single rank only (capturing NCCL send/recv hung at 2 GPUs in round 1), opt-in otherwise.
+        default_graph = "1" if (self.transport == "peer" or self.world == 1) else "0"
+        self._graph_mode = os.environ.get("U1_SLAB_GRAPH", default_graph) == "1"
         self._graph = None
         self._eager_calls = 0
         self.graph_error: Optional[str] = None
 
     def initialize(self) -> torch.Tensor:
         return torch.zeros(2, self.Lx, self.L, dtype=torch.float64, device=self._dev)
+
+    def close(self):
+        self._graph = None
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
+
+    def check_peers(self) -> None:
+        """Host sync + read of the own peer region's error word; raises if a bounded wait on a peer timed out."""
+        if self.peers is None:
+            return
+        torch.cuda.synchronize(self._dev)
+        st = self.peers.status()
+        if st["error"]:
+            raise _lib.U1Error(f"slab peer exchange timed out (error word {st['error']}, rank {self.rank})")
 
     # -- pieces ---------------------------------------------------------------------------
     def _call(self, status, what):
@@ -140,14 +294,14 @@ class SlabHMC:
         """One Metropolis step.  theta_own [2,Lx,L] (this rank's rows, contiguous fp64 on the device) is
         updated in place.  Returns 1-element device tensors dH, accept, H, plaq, topo (no host sync).
 
-        After two eager trajectories the whole step (about 25 kernel launches, the halo exchanges and the
-        all-reduce) is captured once into a CUDA graph and replayed: the trajectory index lives in a
-        device counter that the graph increments (u1_momenta_rows_dev / u1_metropolis_sums_dev), so the
-        replay draws fresh momenta and a fresh accept uniform.  `U1_SLAB_GRAPH=0`, an injected `u`, or a
-        failed capture keep the eager path; with more than one rank the graph path is opt-in
-        (`U1_SLAB_GRAPH=1`): capturing the NCCL send/recv of the halo exchange is not validated."""
+        After two eager trajectories the whole step (about 30 kernel launches including the halo exchanges
+        and the cross-rank Metropolis decision) is captured once into a CUDA graph and replayed: the
+        trajectory index lives in a device counter that the graph increments (u1_momenta_rows_dev /
+        u1_slab_metropolis_peer) and the exchange epochs in the peer region, so the replay draws fresh momenta
+        and a fresh accept uniform.  `U1_SLAB_GRAPH=0`, an injected `u`, or a failed capture keep the eager
+        path.  Every rank must call trajectory() the same number of times."""
         if self._graph_mode and u is None and theta_own.is_cuda:
-            key = (theta_own.data_ptr(), tuple(theta_own.shape))
+            key = (theta_own.data_ptr(), tuple(theta_own.shape), torch.cuda.current_stream(self._dev).cuda_stream)
             g = self._graph
             if g is not None and g["key"] == key:
                 return self._replay(g)
@@ -172,9 +326,9 @@ class SlabHMC:
             with torch.cuda.device(dev):
                 ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # trajectories since capture
                 l0, e0, b0, t0 = self.gpu_launches, self.halo.n_exchanges, self.halo.bytes_sent, self.traj_counter
-                torch.cuda.synchronize(dev)
+                torch.cuda.current_stream(dev).synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                with torch.cuda.graph(graph, stream=None, capture_error_mode="thread_local"):
                     out = self._trajectory_body(theta_own, None, t0, ctr)
                     ctr += 1
             g = {"key": key, "graph": graph, "out": out, "ctr": ctr, "launches": self.gpu_launches - l0,
@@ -189,34 +343,45 @@ class SlabHMC:
             self.graph_error = f"{type(e).__name__}: {e}"
             return None
 
+    def _exchange(self, cur: torch.Tensor, with_pi: bool, rows_up: int, rows_dn: int, sp: int) -> None:
+        """Halo exchange of the extended buffer `cur` [2 fields][2][Lx+2k][L]."""
+        k, Lx, L = self.k, self.Lx, self.L
+        if self.transport == "peer":
+            p = self.peers
+            self._call(self._lib.u1_slab_exchange(cur[0].data_ptr(), cur[1].data_ptr() if with_pi else None, Lx, k, L,
+                                                  rows_up, rows_dn, p.ptrs[p.rank], p.ptrs[(p.rank - 1) % p.world],
+                                                  p.ptrs[(p.rank + 1) % p.world], sp), "u1_slab_exchange")
+            self.halo.n_exchanges += 1
+            self.halo.bytes_sent += (4 if with_pi else 2) * (rows_up + rows_dn) * L * 8
+        else:
+            self.halo.exchange(cur if with_pi else cur[0])
+
     def _trajectory_body(self, theta_own: torch.Tensor, u: Optional[float], traj: int,
                          ctr: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """All device work of one trajectory, operating in place on the halo-extended buffers (no packing
-        copies apart from the halo send buffers): 1 copy-in, momenta, theta halo exchange, H_old sums, blocks
-        of <= k fused steps with a (theta,pi) exchange in between, final drift in place, theta halo exchange,
-        H_new sums, ONE all-reduce of the six sums, Metropolis, select."""
+        """All device work of one trajectory, operating in place on the halo-extended buffers: copy-in,
+        momenta, theta halo exchange, H_old sums, blocks of <= k fused steps with a (theta,pi) exchange in
+        between, final drift in place, one-row theta exchange, H_new sums, cross-rank sum + Metropolis, select."""
         L, Lx, k, dt = self.L, self.Lx, self.k, self.dt
         lib, dev = self._lib, self._dev
         ctr_p = None if ctr is None else ctr.data_ptr()
         cur, nxt = self._ext
-        own = slice(k, k + Lx)
         plane = (Lx + 2 * k) * L                             # doubles between the mu planes of an ext buffer
-        n_own = Lx * L
         s6 = self._sums6
+        peer = self.transport == "peer"
         with torch.cuda.device(dev):
             sp = stream_ptr(dev)
-            ws, nb = WS.get(dev, 4096 + 24 * (Lx + 2), "slab")     # up to one partial triple per row
-            cur[0, :, own] = theta_own
+            ws, nb = self._ws.data_ptr(), self._ws.numel()
+            self._call(lib.u1_slab_copy_in(theta_own.data_ptr(), cur[0, 0, k].data_ptr(), plane, Lx, L, sp), "u1_slab_copy_in")
             # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
             self._call(lib.u1_momenta_rows_dev(cur[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
                                                Lx + 2 * k, L, L, sp), "u1_momenta_rows")
-            self.halo.exchange(cur[0])                      # theta halos
+            self._exchange(cur, False, k, k, sp)             # theta halos
             self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
                                             s6[0:3].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
             done = 0
             while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
                 if done > 0:
-                    self.halo.exchange(cur)                  # theta and pi, k rows each side
+                    self._exchange(cur, True, k, k, sp)      # theta and pi, k rows each side
                 nblk = min(k, self.n_steps - done)
                 in_b = C.c_int(0)
                 self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
@@ -227,27 +392,35 @@ class SlabHMC:
                     cur, nxt = nxt, cur
                 done += nblk
             # final half drift + wrap on own rows, in place (hmc_u1.py:78-79), then H_new
-            for mu in range(2):
-                t = cur[0, mu, k].data_ptr()
-                self._call(lib.u1_drift_wrap(t, cur[1, mu, k].data_ptr(), t, 0.5 * dt, n_own, sp), "u1_drift_wrap")
-            self.halo.exchange(cur[0])
+            self._call(lib.u1_slab_drift_wrap(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane, Lx, L, 0.5 * dt, sp),
+                       "u1_slab_drift_wrap")
+            if peer:
+                self._exchange(cur, False, 1, 0, sp)         # H_new only reads the lower neighbour's first row
+            else:
+                self._exchange(cur, False, k, k, sp)
             self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
                                             s6[3:6].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
-            if self.world > 1:
-                dist.all_reduce(s6, group=self.group)
-            # every rank takes the same decision from the all-reduced sums and the shared Philox draw
             out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
             out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
             u_d = None if u is None else torch.tensor([float(u)], dtype=torch.float64, device=dev)
-            self._call(lib.u1_metropolis_sums_dev(s6[0:3].data_ptr(), s6[3:6].data_ptr(),
-                                                  None if u_d is None else u_d.data_ptr(),
-                                                  self.seed, self.chain, traj, ctr_p, 1, self.beta, float(L) * L,
-                                                  out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
-                                                  out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
-                       "u1_metropolis_sums")
-            for mu in range(2):
-                self._call(lib.u1_select_accepted(theta_own[mu].data_ptr(), cur[0, mu, k].data_ptr(),
-                                                  out["accept"].data_ptr(), n_own, 1, sp), "u1_select_accepted")
+            if peer:
+                # all ranks' sums gathered through the peer regions and added in rank order inside the kernel
+                self._call(lib.u1_slab_metropolis_peer(
+                    s6[0:3].data_ptr(), s6[3:6].data_ptr(), None if u_d is None else u_d.data_ptr(), self.seed,
+                    self.chain, traj, ctr_p, self.beta, float(L) * L, self.rank, self.world, self.peers.table,
+                    out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(), out["plaq"].data_ptr(),
+                    out["topo"].data_ptr(), sp), "u1_slab_metropolis_peer")
+            else:
+                if self.world > 1:
+                    dist.all_reduce(s6, group=self.group)
+                self._call(lib.u1_metropolis_sums_dev(s6[0:3].data_ptr(), s6[3:6].data_ptr(),
+                                                      None if u_d is None else u_d.data_ptr(),
+                                                      self.seed, self.chain, traj, ctr_p, 1, self.beta, float(L) * L,
+                                                      out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
+                                                      out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
+                           "u1_metropolis_sums")
+            self._call(lib.u1_slab_select(theta_own.data_ptr(), cur[0, 0, k].data_ptr(), plane, Lx, L,
+                                          out["accept"].data_ptr(), sp), "u1_slab_select")
         if ctr is None:
             # (under capture the buffer roles must stay as they were: every replay starts from them)
             self._ext = [cur, nxt]

@@ -179,6 +179,53 @@ int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, 
 int u1_slab_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* sums,
                      int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
 
+/* ---------------- NVLink peer path of the slab decomposition (csrc/u1_slab.cu) ----------------
+ * The reference has no multi-GPU path; these entry points replace what a torch.distributed
+ * implementation of SURVEY §8(e) would do with ncclSend/ncclRecv + ncclAllReduce per exchange: the kernels
+ * store halo rows and Hamiltonian sums directly into the neighbours' memory over NVLink and synchronise
+ * through epoch flags, so a trajectory needs no host-driven collective and can be captured in one CUDA graph.
+ *
+ * Peer region: u1_slab_peer_region_bytes(k, L) bytes of zero-initialised device memory per rank, allocated by
+ * u1_peer_alloc (cudaMalloc; the only entry points that allocate - the memory must be IPC-exportable, which a
+ * caching allocator's sub-blocks are not).  ipc_handle_out (may be NULL) receives u1_ipc_handle_bytes() bytes
+ * that another process of the same box passes to u1_peer_open to map the region (cudaIpcOpenMemHandle, peer
+ * access enabled lazily).  Within one process the pointers can be used directly. */
+size_t u1_ipc_handle_bytes(void);
+size_t u1_slab_peer_region_bytes(int k, int L);
+int u1_peer_alloc(void** dev_ptr, size_t bytes, void* ipc_handle_out);
+int u1_peer_open(const void* ipc_handle, void** dev_ptr);
+int u1_peer_close(void* dev_ptr);
+int u1_peer_free(void* dev_ptr);
+/* First 8 control words of a region copied to the host (synchronous): [0] top flag, [1] bottom flag,
+ * [2] exchange epoch, [5] Metropolis epoch, [6] error word (non-zero: a bounded wait on a peer timed out). */
+int u1_slab_peer_status(const void* region_self, unsigned long long* host_words8);
+/* Ring halo exchange of an extended slab ext[2][Lx+2k][L] (own rows k..k+Lx-1): my first rows_up own rows become
+ * the bottom halo of rank-1 (region_up), my last rows_dn own rows the top halo of rank+1 (region_dn); the same
+ * call on the neighbours fills my halos.  rows_* <= k, adjacent to the own rows.  ext_pi may be NULL (theta only).
+ * One kernel launch: push over NVLink, st.release.sys epoch flag, bounded wait, unpack.  World size 1: pass the
+ * own region three times (periodic wrap). */
+int u1_slab_exchange(double* ext_theta, double* ext_pi, int Lx, int k, int L, int rows_up, int rows_dn,
+                     void* region_self, void* region_up, void* region_dn, u1_stream_t stream);
+/* hmc_u1.py:84-97 for a decomposed lattice: all-gather of every rank's Hamiltonian sums ([3] old, [3] new, as
+ * u1_slab_sums_ext produces them) through the peer regions (regions: HOST array of `world` device pointers,
+ * regions[rank] is the caller's own), summed in rank order so that every rank forms bit-identical totals, then
+ * the Metropolis decision with the shared draw Philox(seed, chain, traj + *traj_dev) or u_inject[0].
+ * Outputs are single elements; out_accept is required. */
+int u1_slab_metropolis_peer(const double* sums_old, const double* sums_new, const double* u_inject,
+                            uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
+                            double beta, double volume, int rank, int world, void* const* regions,
+                            double* out_dH, int32_t* out_accept, double* out_H, double* out_plaq, double* out_topo,
+                            u1_stream_t stream);
+/* In-place helpers on the own rows of an extended buffer (both mu planes in one launch; *_own point at the first
+ * own row of the mu=0 plane, the mu=1 plane lies plane_stride doubles further):
+ *   drift_wrap: theta = regularize(theta + a*pi)   (hmc_u1.py:78-79)
+ *   copy_in:    ext = theta_own [2][Lx][L]          select: theta_own = ext where *accept != 0 */
+int u1_slab_drift_wrap(double* ext_theta_own, const double* ext_pi_own, size_t plane_stride, int Lx, int L, double a,
+                       u1_stream_t stream);
+int u1_slab_copy_in(const double* theta_own, double* ext_theta_own, size_t plane_stride, int Lx, int L, u1_stream_t stream);
+int u1_slab_select(double* theta_own, const double* ext_theta_own, size_t plane_stride, int Lx, int L,
+                   const int32_t* accept, u1_stream_t stream);
+
 /* Training-loss reduction (field_trans_opt.py:452-458): out4[k] = sum_i |a[i]-b[i]|^(2k+2), k = 0..3, over n
  * doubles (deterministic two-phase reduction; out4 is device memory).  The loss is
  * sum_k out4[k]^(1/p_k) / vol^(1/p_k), p_k = 2,4,6,8, formed by the caller. */

@@ -1,5 +1,11 @@
-"""torchrun worker: slab-decomposed plain HMC over WORLD_SIZE GPUs against the undecomposed chain
-computed on rank 0 with the streaming path of HMC_U1.  Prints 'SLAB_OK' on success."""
+"""Worker for the slab-decomposed plain HMC tests (BASELINE configs[4] path) against the undecomposed chain
+(streaming path of HMC_U1 on one GPU).  Prints 'SLAB_OK' on success.
+
+    python slab_worker.py L halo [transport] [virtual_ranks]
+      under torchrun: WORLD_SIZE real ranks, one GPU each (transport peer = CUDA IPC + NVLink, or nccl)
+      alone, virtual_ranks = R > 1: R ranks inside this process on ONE GPU (PeerRegions.local), each on its own
+      stream - the same kernels, flags and graphs as the multi-GPU path, checkable on a 1-GPU box.
+The run is 6 trajectories, so with graphs on (default) it covers 2 eager passes, the capture and 4 replays."""
 import os
 import sys
 
@@ -9,44 +15,76 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import hmc_ft_b200 as hb  # noqa: E402
-from hmc_ft_b200.sharding import SlabHMC  # noqa: E402
+from hmc_ft_b200.sharding import PeerRegions, SlabHMC  # noqa: E402
 
 
 def main():
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     halo = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    n_traj, n_steps, dt, beta = 3, 8, 0.1, 4.0
+    transport = sys.argv[3] if len(sys.argv) > 3 else "peer"
+    virt = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    n_traj, n_steps, dt, beta = 6, 9, 0.1, 4.0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank() if world > 1 else 0
-    slab = SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0)
     g = torch.Generator().manual_seed(5)
     full0 = (torch.rand(2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * 3.0
-    own = full0[:, rank * slab.Lx:(rank + 1) * slab.Lx].contiguous().cuda()
-    outs = [slab.trajectory(own) for _ in range(n_traj)]
-    torch.cuda.synchronize()
-    # reference: the same chain undecomposed (rank 0 only needs it, every rank computes it cheaply)
+    if virt > 1:
+        assert world == 1
+        k = max(1, min(halo, L // virt, n_steps))
+        regs = PeerRegions.local(virt, k, L)
+        slabs = [SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0, transport="peer", peers=regs[r]) for r in range(virt)]
+        streams = [torch.cuda.Stream() for _ in range(virt)]
+        owns = [full0[:, r * s.Lx:(r + 1) * s.Lx].contiguous().cuda() for r, s in enumerate(slabs)]
+        torch.cuda.synchronize()
+        outs = [[] for _ in range(virt)]
+        for _ in range(n_traj):
+            for r in range(virt):
+                with torch.cuda.stream(streams[r]):
+                    outs[r].append(slabs[r].trajectory(owns[r]))
+        torch.cuda.synchronize()
+        for s in slabs:
+            s.check_peers()
+            assert s.graph_error is None, s.graph_error
+    else:
+        slabs = [SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0, transport=transport)]
+        owns = [full0[:, rank * slabs[0].Lx:(rank + 1) * slabs[0].Lx].contiguous().cuda()]
+        outs = [[slabs[0].trajectory(owns[0]) for _ in range(n_traj)]]
+        torch.cuda.synchronize()
+        slabs[0].check_peers()
+        assert slabs[0].graph_error is None, slabs[0].graph_error
+    # reference: the same chain undecomposed
     ref = hb.HMC_U1(L, beta, 0, n_steps, dt, device="cuda", if_tune_step_size=False, n_chains=1, seed=1331,
                     kernel_path=1)
     th = full0.cuda()[None].clone()
     r = ref.trajectories(th, n_traj)
-    for t in range(n_traj):
-        assert abs(outs[t]["dH"].item() - r["dH"][t, 0].item()) < 1e-8, (t, outs[t]["dH"].item(), r["dH"][t, 0].item())
-        assert int(outs[t]["accept"].item()) == int(r["accept"][t, 0].item())
-        assert abs(outs[t]["plaq"].item() - r["plaq"][t, 0].item()) < 1e-12
-        assert outs[t]["topo"].item() == r["topo"][t, 0].item()
-    want = th[0][:, rank * slab.Lx:(rank + 1) * slab.Lx]
-    err = (own - want).abs().max().item()
-    assert err < 1e-10, err
-    assert slab.halo.n_exchanges >= n_traj * (2 + (n_steps - 1) // slab.k)
+    worst = 0.0
+    n_acc = 0
+    for i, (slab, own, out) in enumerate(zip(slabs, owns, outs)):
+        rk = slab.rank
+        for t in range(n_traj):
+            assert abs(out[t]["dH"].item() - r["dH"][t, 0].item()) < 1e-8, (t, out[t]["dH"].item(), r["dH"][t, 0].item())
+            assert int(out[t]["accept"].item()) == int(r["accept"][t, 0].item())
+            assert abs(out[t]["plaq"].item() - r["plaq"][t, 0].item()) < 1e-12
+            assert out[t]["topo"].item() == r["topo"][t, 0].item()
+            n_acc += int(out[t]["accept"].item())
+        want = th[0][:, rk * slab.Lx:(rk + 1) * slab.Lx]
+        err = (own - want).abs().max().item()
+        assert err < 1e-10, err
+        worst = max(worst, err)
+        assert slab.halo.n_exchanges >= n_traj * (2 + (n_steps - 1) // slab.k)
+        if slab._graph_mode:
+            assert slab._graph is not None, "graph was not captured"
+    assert 0 < n_acc < n_traj * len(slabs) or n_traj < 4, "want both accepted and rejected steps in the sample"
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print("SLAB_OK world", world, "L", L, "halo", slab.k, "max|dtheta|", err)
+        print("SLAB_OK world", world, "virtual", virt, "L", L, "halo", slabs[0].k, "transport", slabs[0].transport,
+              "graph", slabs[0]._graph is not None, "max|dtheta|", worst)
 
 
 if __name__ == "__main__":

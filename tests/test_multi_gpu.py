@@ -11,18 +11,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
 
 
-@pytest.mark.parametrize("L,halo", [(64, 1), (128, 3), (96, 8)])
-def test_slab_world1_matches_plain_chain(L, halo):
-    out = subprocess.run([sys.executable, WORKER, str(L), str(halo)], capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("L,halo,transport", [(64, 1, "peer"), (128, 3, "peer"), (96, 8, "peer"), (128, 3, "nccl")])
+def test_slab_world1_matches_plain_chain(L, halo, transport):
+    out = subprocess.run([sys.executable, WORKER, str(L), str(halo), transport], capture_output=True, text=True, timeout=600)
     assert "SLAB_OK" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_multi_gpu_matches_plain_chain(world):
+@pytest.mark.parametrize("L,halo,virt", [(128, 4, 2), (256, 4, 4), (192, 2, 3), (512, 16, 8)])
+def test_slab_virtual_ranks_on_one_gpu(L, halo, virt):
+    """The NVLink peer path (push kernels, epoch flags, cross-rank Metropolis, CUDA-graph replay) with several
+    ranks inside one process on ONE GPU: same code as the multi-GPU run, checkable where only one GPU exists."""
+    out = subprocess.run([sys.executable, WORKER, str(L), str(halo), "peer", str(virt)], capture_output=True, text=True,
+                         timeout=600)
+    assert "SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("world,transport", [(2, "peer"), (4, "peer"), (8, "peer"), (2, "nccl"), (8, "nccl")])
+def test_slab_multi_gpu_matches_plain_chain(world, transport):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29631", WORKER, "256", "4"],
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", WORKER, "256", "4", transport],
                          capture_output=True, text=True, timeout=900)
     assert "SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
