@@ -48,6 +48,8 @@ SIGNATURES = {
     "u1_peer_open": (_i, [_vp, C.POINTER(_vp)]),
     "u1_peer_close": (_i, [_vp]),
     "u1_peer_free": (_i, [_vp]),
+    "u1_slab_preload": (_i, []),
+    "u1_plain_preload_slab_kernels": (_i, []),
     "u1_slab_peer_status": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
     "u1_slab_exchange": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "u1_slab_metropolis_peer": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _d, _d, _i, _i, C.POINTER(_vp),
@@ -61,6 +63,7 @@ SIGNATURES = {
     "u1ft_destroy": (_i, [_vp]),
     "u1ft_weight_count": (_sz, [_i]),
     "u1ft_set_chunk_sites": (C.c_longlong, [C.c_longlong]),
+    "u1ft_last_host_launch_count": (C.c_longlong, []),
     "u1ft_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "u1ft_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "u1ft_phase": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),

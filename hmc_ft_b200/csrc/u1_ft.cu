@@ -18,6 +18,7 @@
 #include <vector>
 #include <cstdlib>
 #include <atomic>
+#include <mutex>
 #include "u1_common.cuh"
 
 namespace u1 {
@@ -655,21 +656,27 @@ __global__ void __launch_bounds__(256) k_sum_pairs(const double* __restrict__ pa
     if (threadIdx.x == 0) { norms[0] = v[0]; norms[1] = v[1]; }
 }
 
-// logdet[b] (+)= sum of partials, fixed order.
-__global__ void k_ft_logdet_accum(const double* __restrict__ partial, double* __restrict__ logdet,
-                                  int B, int nblk, int first) {
+// logdet[b] = sum over the 8 subsets (in order) of the fixed-order sum of that subset's block partials.
+// partial: [8][B][nblk].  Same association as accumulating subset by subset.
+__global__ void k_ft_logdet_accum(const double* __restrict__ partial, double* __restrict__ logdet, int B, int nblk) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += partial[(size_t)b * nblk + i];
-    logdet[b] = first ? s : logdet[b] + s;
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) {
+        const double* p = partial + ((size_t)k * B + b) * nblk;
+        double s = 0.0;
+        for (int i = 0; i < nblk; ++i) s += p[i];
+        tot = (k == 0) ? s : tot + s;
+    }
+    logdet[b] = tot;
 }
 
 // ---------------------------------------------------------------------------------------
 // Reverse pass of one subset.
 //   g      : dS/dtheta^(k+1)                         [B][2][V]
 //   zbar   : adjoint of the final conv's pre-activation  [B][12][V]  (written densely)
-//   AP, AR : adjoints of the plaquette / (update-type) rectangle angles, [B][V], pre-zeroed
+//   AP, AR : adjoints of the plaquette / (update-type) rectangle angles, [B][V] (AR: every entry written;
+//            AP: written on the complement of the CNN plaquette mask, the rest is never read)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kUpdThreads)
 k_ft_update_bwd(const double* __restrict__ th, const double* __restrict__ K,
@@ -727,8 +734,11 @@ __global__ void k_ft_feat_bwd(const double* __restrict__ th, const double* __res
     Lat g{t0, t0 + V, L};
     const double* xb = Xbar + (size_t)b * kXC * V;
     const double* ARb = AR + (size_t)b * V;
-    double pt = AP[(size_t)b * V + r];
+    // AP (adjoint of the update's plaquette angles) is written by k_ft_update_bwd exactly on the plaquettes that
+    // touch an active link - the complement of the CNN plaquette mask mP - and AR on every site, so neither
+    // buffer needs zeroing between subsets: unwritten AP entries are simply not read.
     const bool mP = ss.mu == 0 ? ((x & 1) != ss.a) : ((y & 1) != ss.b);
+    double pt = mP ? 0.0 : AP[(size_t)b * V + r];
     if (mP) {
         double sn, cs;
         fast_sincos(g.P(x, y), sn, cs);
@@ -889,6 +899,17 @@ struct u1ft_handle_s {
     cudaStream_t lane[kLanes];                            // internal streams of u1ft_trajectory (lazy)
     cudaEvent_t ev_fork, ev_join[kLanes];
     bool lanes_ready;
+    // CUDA-graph cache of the trajectory building blocks (one FT force + kick: ~170 kernel nodes with their
+    // programmatic-dependent-launch edges; one forward + action), keyed by workspace / shape / parameters
+    struct GraphEntry {
+        int kind; void* ws; int C, L; double beta, dt;
+        cudaGraphExec_t exec; long long kernels; unsigned long long stamp;
+    };
+    std::vector<GraphEntry> graphs;
+    std::mutex graph_mu;
+    unsigned long long graph_clock;
+    bool graphs_broken;                                   // a capture failed once: stay on eager launches
+    cudaStream_t cap_stream;                              // side stream used only for capturing (lazy)
 };
 
 static int ensure_lanes(u1ft_handle_s* h) {
@@ -979,7 +1000,7 @@ struct FtWs {
     double* D;            // GELU' per subset per layer       [8][n_layers][C][12][V]
     double* AP; double* AR; double* PT;                      // [C][V]
     double* g0; double* g1;                                   // adjoint ping-pong [C][2][V]
-    double* partial;      // logdet partials                  [C][nblk]
+    double* partial;      // logdet partials                  [8][C][nblk]
     double* logdet; double* sums_old; double* sums_new; double* H_old; double* H_new;   // [C](x3)
     double* th_new; double* pi; double* force;                // trajectory state  [C][2][V]
     int32_t* acc;
@@ -996,7 +1017,7 @@ static FtWs carve_ft(void* ws, int n_layers, int C, int L, bool backward) {
     auto take = [&](size_t n) { double* r = (double*)p; p += n; return r; };
     for (int i = 0; i < 9; ++i) w.th[i] = take(f2);
     w.X = take(f6); w.A = take(f12); w.Bf = take(f12);
-    w.partial = take(al((size_t)C * nblk * 8));
+    w.partial = take(al((size_t)8 * C * nblk * 8));                   // [8 subsets][C][nblk]
     w.logdet = take(al((size_t)C * 8));
     w.sums_old = take(al((size_t)C * 3 * 8)); w.sums_new = take(al((size_t)C * 3 * 8));
     w.H_old = take(al((size_t)C * 8)); w.H_new = take(al((size_t)C * 8));
@@ -1156,14 +1177,14 @@ static int ft_forward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, bool s
         U1_CHECK_LAUNCH();
         U1_TRY(cnn_forward(h, w, k, C, L, store, st));
         k_ft_update<<<dim3(nblk, C), kUpdThreads, 0, st>>>(w.th[k], w.Kk[k], w.th[k + 1],
-                                                           want_logdet ? w.partial : nullptr, k, L, nblk, 0);
+                                                           want_logdet ? w.partial + (size_t)k * C * nblk : nullptr, k, L, nblk, 0);
         count_launch();
         U1_CHECK_LAUNCH();
-        if (want_logdet) {
-            k_ft_logdet_accum<<<blocks_for(C, 128), 128, 0, st>>>(w.partial, w.logdet, C, nblk, k == 0);
-            count_launch();
-            U1_CHECK_LAUNCH();
-        }
+    }
+    if (want_logdet) {
+        k_ft_logdet_accum<<<blocks_for(C, 128), 128, 0, st>>>(w.partial, w.logdet, C, nblk);
+        count_launch();
+        U1_CHECK_LAUNCH();
     }
     return U1_OK;
 }
@@ -1189,10 +1210,6 @@ static int ft_backward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, doubl
     count_launch();
     U1_CHECK_LAUNCH();
     for (int k = 7; k >= 0; --k) {
-        cudaError_t e = cudaMemsetAsync(w.AP, 0, (size_t)C * V * 8, st);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaMemsetAsync(w.AR, 0, (size_t)C * V * 8, st);
-        if (e != cudaSuccess) return (int)e;
         k_ft_update_bwd<<<blocks_for(ns, kUpdThreads), kUpdThreads, 0, st>>>(
             w.th[k], w.Kk[k], Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1), g, w.A, w.AP, w.AR, k, ns, L);
         count_launch();
@@ -1228,7 +1245,84 @@ static int ft_force_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double b
     return ft_backward_chunk(h, w, C, L, beta, result, st);
 }
 
+// ---------------------------------------------------------------------------------------
+// CUDA graphs of the trajectory building blocks.  A 50-step FT trajectory is ~9 000 kernel launches of 10 KB
+// parameters each; at small per-GPU batches (128 chains at 8 GPUs, or L=32) the kernels are shorter than the
+// ~6 us the host needs per launch, so the GPU starves.  The force + kick of one leapfrog step (and the
+// forward + action pass of H_old / H_new) are captured once per (workspace, chunk shape, beta, dt) with their
+// programmatic-dependent-launch edges and replayed: ~110 host launches per trajectory instead of ~9 000.
+// U1FT_GRAPH=0 keeps eager launches; a stream that is already being captured by the caller is left alone.
+// ---------------------------------------------------------------------------------------
+thread_local long long g_graph_kernels = 0;      // kernels of this call that ran inside graph replays
+thread_local long long g_graph_replays = 0;      // graph launches of this call
+enum { GRAPH_FORCE_KICK = 1, GRAPH_ACTION = 2 };
+constexpr size_t kMaxGraphs = 12;
+
+static bool graphs_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_GRAPH"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
+// Runs body(stream) - a sequence of kernel launches - either eagerly on st or as a cached graph replayed on st.
+// The capture happens on a handle-owned side stream: the caller's stream may be the legacy default stream
+// (torch's default), which cannot be captured.
+template <class Body>
+static int run_graphed(u1ft_handle_s* h, int kind, void* ws, int C, int L, double beta, double dt, cudaStream_t st, Body body) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool usable = graphs_enabled() && !h->graphs_broken && cudaStreamIsCapturing(st, &cs) == cudaSuccess &&
+                        cs == cudaStreamCaptureStatusNone;
+    if (!usable) { cudaGetLastError(); return body(st); }
+    cudaGraphExec_t exec = nullptr;
+    long long kernels = 0;
+    {
+        std::lock_guard<std::mutex> lk(h->graph_mu);
+        for (auto& g : h->graphs)
+            if (g.kind == kind && g.ws == ws && g.C == C && g.L == L && g.beta == beta && g.dt == dt) {
+                g.stamp = ++h->graph_clock;
+                exec = g.exec; kernels = g.kernels;
+                break;
+            }
+        if (!exec) {
+            auto broken = [&]() { cudaGetLastError(); h->graphs_broken = true; };
+            if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) broken();
+            const long long k0 = g_launches;
+            if (!h->graphs_broken && cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) broken();
+            if (!h->graphs_broken) {
+                const int r = body(h->cap_stream);             // recorded, not executed
+                cudaGraph_t graph = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+                kernels = g_launches - k0;
+                g_launches = k0;                                 // the replay below accounts for the kernels
+                if (r != U1_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+                    exec = nullptr;
+                    broken();
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (exec) {
+                if (h->graphs.size() >= kMaxGraphs) {            // evict the least recently used entry
+                    size_t lru = 0;
+                    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+                    cudaGraphExecDestroy(h->graphs[lru].exec);
+                    h->graphs.erase(h->graphs.begin() + lru);
+                }
+                h->graphs.push_back({kind, ws, C, L, beta, dt, exec, kernels, ++h->graph_clock});
+            }
+        }
+    }
+    if (!exec) return body(st);                                  // capture unavailable: eager launches, for good
+    const cudaError_t e = cudaGraphLaunch(exec, st);
+    if (e != cudaSuccess) return (int)e;
+    count_launch((int)kernels);
+    g_graph_kernels += kernels;
+    g_graph_replays += 1;
+    return U1_OK;
+}
+
 extern "C" {
+
+long long u1ft_last_host_launch_count(void) { return g_launches - g_graph_kernels + g_graph_replays; }
 
 long long u1ft_set_chunk_sites(long long sites) {
     const long long prev = g_chunk_explicit.load() ? chunk_sites() : 0;     // 0 = automatic (wave-aware) choice
@@ -1255,6 +1349,9 @@ int u1ft_create(u1ft_handle_t* out, int n_res, const double* weights, size_t n_d
     if (!h) return U1_ERR_HANDLE;
     h->magic = kMagic; h->n_res = n_res; h->n_layers = 2 + 2 * n_res;
     h->lanes_ready = false;
+    h->graph_clock = 0;
+    h->graphs_broken = false;
+    h->cap_stream = nullptr;
     const int nl = h->n_layers;
     h->fs.resize(8);
     h->f0.resize(8); h->b0.resize(8); h->f.resize((size_t)8 * (nl - 1)); h->bt.resize((size_t)8 * (nl - 1));
@@ -1324,6 +1421,9 @@ int u1ft_destroy(u1ft_handle_t h) {
     cudaGetDevice(&prev);
     if (prev != h->device) cudaSetDevice(h->device);     // free on the device that owns the table / streams
     if (h->gelu_tab) cudaFree(h->gelu_tab);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->lanes_ready) {
         cudaEventDestroy(h->ev_fork);
         for (int l = 0; l < kLanes; ++l) { cudaStreamDestroy(h->lane[l]); cudaEventDestroy(h->ev_join[l]); }
@@ -1341,6 +1441,8 @@ size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward) {
 int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
                  int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1362,6 +1464,8 @@ int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double
 int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
                int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !delta || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1389,6 +1493,8 @@ int u1ft_phase(u1ft_handle_t h, const double* theta, int index, double* delta,
 int u1ft_coefficients(u1ft_handle_t h, const double* theta, int index, double* K,
                       int B, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !K || B <= 0 || L <= 0 || index < 0 || index > 7) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1418,6 +1524,8 @@ int u1ft_inverse_iter(const double* theta_curr, const double* theta_iter, const 
                       double* theta_next, double* norms, int B, int L,
                       void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!theta_curr || !theta_iter || !K || !theta_next || !norms || B <= 0 || L <= 0 || index < 0 || index > 7)
         return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1438,6 +1546,8 @@ int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* thet
                 double* logdet, int B, int L, double beta,
                 void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !S_ft || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1460,6 +1570,8 @@ int u1ft_action(u1ft_handle_t h, const double* theta, double* S_ft, double* thet
 int u1ft_force(u1ft_handle_t h, const double* theta, double* force, double* S_ft,
                int B, int L, double beta, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || !force || B <= 0 || L <= 0) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1482,15 +1594,19 @@ int u1ft_force(u1ft_handle_t h, const double* theta, double* force, double* S_ft
 static int ft_leapfrog_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, double beta, double dt,
                              int n_steps, cudaStream_t st) {
     const size_t n = (size_t)C * 2 * L * L;
+    auto force_kick = [&](cudaStream_t s) -> int {   // pi -= dt * dS_FT/dtheta(theta): one graph replay per step
+        double* F = nullptr;
+        U1_TRY(ft_force_chunk(h, w, C, L, beta, nullptr, &F, s));
+        k_axpy<<<ew_grid_ft(n), 256, 0, s>>>(w.pi, F, -dt, n);
+        count_launch();
+        U1_CHECK_LAUNCH();
+        return U1_OK;
+    };
     for (int s = 0; s < n_steps; ++s) {
         k_axpy<<<ew_grid_ft(n), 256, 0, st>>>(w.th[0], w.pi, s == 0 ? 0.5 * dt : dt, n);
         count_launch();
         U1_CHECK_LAUNCH();
-        double* F = nullptr;
-        U1_TRY(ft_force_chunk(h, w, C, L, beta, nullptr, &F, st));
-        k_axpy<<<ew_grid_ft(n), 256, 0, st>>>(w.pi, F, -dt, n);
-        count_launch();
-        U1_CHECK_LAUNCH();
+        U1_TRY(run_graphed(h, GRAPH_FORCE_KICK, (void*)w.th[0], C, L, beta, dt, st, force_kick));
     }
     k_axpy_wrap<<<ew_grid_ft(n), 256, 0, st>>>(w.th[0], w.pi, 0.5 * dt, n);
     count_launch();
@@ -1502,6 +1618,8 @@ int u1ft_leapfrog(u1ft_handle_t h, const double* theta_in, const double* pi_in,
                   double* theta_out, double* pi_out, int B, int L, double beta, double dt,
                   int n_steps, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta_in || !pi_in || !theta_out || !pi_out || B <= 0 || L <= 0 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1528,6 +1646,8 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
                     double* out_topo, double* theta_ori_out,
                     void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
+    g_graph_kernels = 0;
+    g_graph_replays = 0;
     if (!handle_ok(h) || !handle_on_current_device(h)) return U1_ERR_HANDLE;
     if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
@@ -1570,16 +1690,20 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
             }
             // H_old (hmc_u1_ft.py:196-197)
             U1_TRY(copy_async(w.th[0], th_cur, n * 8, st));
-            U1_TRY(ft_forward_chunk(h, w, C, L, false, true, st));
-            U1_TRY(ft_action_chunk(w, C, L, beta, w.pi, w.sums_old, nullptr, w.H_old, st));
+            auto action_pass = [&](cudaStream_t s) -> int {   // theta in w.th[0], momenta in w.pi -> (w.sums_new, w.H_new, w.th[8])
+                U1_TRY(ft_forward_chunk(h, w, C, L, false, true, s));
+                return ft_action_chunk(w, C, L, beta, w.pi, w.sums_new, nullptr, w.H_new, s);
+            };
+            U1_TRY(run_graphed(h, GRAPH_ACTION, (void*)w.th[0], C, L, beta, 0.0, st, action_pass));
+            U1_TRY(copy_async(w.sums_old, w.sums_new, (size_t)C * 3 * 8, st));
+            U1_TRY(copy_async(w.H_old, w.H_new, (size_t)C * 8, st));
             if (theta_ori_out && t == n_traj - 1)            // F(theta_old), kept if the step is rejected
                 U1_TRY(copy_async(theta_ori_out + (size_t)b0 * per, w.th[8], n * 8, st));
             // leapfrog (hmc_u1_ft.py:199)
             U1_TRY(ft_leapfrog_chunk(h, w, C, L, beta, dt, n_steps, st));
             U1_TRY(copy_async(w.th_new, w.th[0], n * 8, st));
             // H_new (hmc_u1_ft.py:200-201)
-            U1_TRY(ft_forward_chunk(h, w, C, L, false, true, st));
-            U1_TRY(ft_action_chunk(w, C, L, beta, w.pi, w.sums_new, nullptr, w.H_new, st));
+            U1_TRY(run_graphed(h, GRAPH_ACTION, (void*)w.th[0], C, L, beta, 0.0, st, action_pass));
             k_ft_metropolis<<<blocks_for(C, 128), 128, 0, st>>>(
                 w.H_old, w.H_new, w.sums_old, w.sums_new, u_inject ? u_inject + o : nullptr, seed,
                 chain0 + b0, traj, C, inv_vol, out_dH ? out_dH + o : nullptr,

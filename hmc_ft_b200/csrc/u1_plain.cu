@@ -1393,6 +1393,21 @@ int u1_slab_sums(const double* theta, const double* theta_dn, const double* pi, 
     return launch_sums(theta, theta_dn, pi, sums, (double*)ws, 1, Lx, L, (cudaStream_t)stream);
 }
 
+int u1_plain_preload_slab_kernels(void) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<32>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<64>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_finish_sums);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_momenta_rows);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_metropolis);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_select);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_final_drift);
+    return e == cudaSuccess ? U1_OK : (int)e;
+}
+
 int u1_slab_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* sums,
                      int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;

@@ -28,7 +28,7 @@ enum : int { W_F_TOP = 0, W_F_BOT = 1, W_C_XCH = 2, W_C_PUSH = 3, W_C_DONE = 4, 
 constexpr int kPeerMaxWorld = 16;
 constexpr size_t kPeerSumsOff = 512;          // [2 parity][16 ranks][8 doubles]
 constexpr size_t kPeerStageOff = 4096;        // [2 parity][2 sides: 0 top-in, 1 bottom-in][4 planes][k*L doubles]
-constexpr unsigned long long kPeerTimeoutNs = 8000000000ull;
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // per wait; the error word is sticky (later waits are skipped)
 
 __host__ __device__ inline size_t peer_stage_doubles(int k, int L) { return (size_t)4 * k * L; }   // one side, one parity
 
@@ -108,9 +108,10 @@ __global__ void __launch_bounds__(kXchThreads) k_slab_exchange(XchArgs a) {
             st_release_sys(a.dn + W_F_TOP, e + 1);
         }
         // ---- wait for the neighbours' rows ----
-        bool ok = wait_flag(a.self + W_F_TOP, e + 1);
-        ok = wait_flag(a.self + W_F_BOT, e + 1) && ok;
-        if (!ok) atomicExch(a.self + W_ERR, 1ull);
+        bool ok = *reinterpret_cast<volatile unsigned long long*>(a.self + W_ERR) == 0ull;     // sticky: no more waiting after a timeout
+        ok = ok && wait_flag(a.self + W_F_TOP, e + 1);
+        ok = ok && wait_flag(a.self + W_F_BOT, e + 1);
+        if (!ok) atomicCAS(a.self + W_ERR, 0ull, 1ull);          // keep the FIRST error code
         s_ok = ok ? 1 : 0;
     }
     __syncthreads();
@@ -160,7 +161,8 @@ k_slab_metropolis_peer(PeerTable pt, int rank, int world, const double* __restri
         for (int i = 0; i < 3; ++i) { slot[i] = s_old[i]; slot[3 + i] = s_new[i]; }
         __threadfence_system();
         st_release_sys(pt.region[r] + W_F_SUM0 + rank, e + 1);
-        if (!wait_flag(self + W_F_SUM0 + r, e + 1)) atomicExch(self + W_ERR, 2ull);
+        if (*reinterpret_cast<volatile unsigned long long*>(self + W_ERR) == 0ull && !wait_flag(self + W_F_SUM0 + r, e + 1))
+            atomicCAS(self + W_ERR, 0ull, 2ull);
     }
     __syncwarp();
     if (r == 0) {
@@ -261,6 +263,21 @@ int u1_peer_free(void* dev_ptr) {
     if (!dev_ptr) return U1_ERR_ARG;
     cudaError_t e = cudaFree(dev_ptr);
     return e == cudaSuccess ? U1_OK : (int)e;
+}
+
+// With lazy module loading (the CUDA 12 default) the FIRST launch of a kernel loads its code, and that load can
+// wait for the device to go idle.  A kernel that spins on a peer's flag must therefore never be the reason a
+// not-yet-loaded kernel of the same trajectory cannot start: load everything the slab trajectory uses up front.
+int u1_plain_preload_slab_kernels(void);                    // u1_plain.cu
+int u1_slab_preload(void) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k_slab_exchange);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_metropolis_peer);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_drift_wrap_planes);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_select_planes);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_copy_in);
+    if (e != cudaSuccess) return (int)e;
+    return u1_plain_preload_slab_kernels();
 }
 
 int u1_slab_peer_status(const void* region_self, unsigned long long* host_words8) {

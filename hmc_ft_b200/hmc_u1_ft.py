@@ -58,6 +58,7 @@ class HMC_U1_FT:
         self.seed, self.chain_offset, self.verbose = int(seed), int(chain_offset), verbose
         self.traj_counter = 0
         self.gpu_launches = 0
+        self.graph_launches = 0
         self._lib = _lib.load()
         self._dev = require_cuda(self.device if self.device.type == "cuda" else None)
         self.ft = _resolve_ft(field_transformation, compute_jac_logdet, self.lattice_size)
@@ -163,6 +164,7 @@ class HMC_U1_FT:
                 out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(), out["plaq"].data_ptr(),
                 out["topo"].data_ptr(), ptr(ori), ws, nb, stream_ptr(dev)), "u1ft_trajectory")
         self.gpu_launches += _lib.last_launch_count()
+        self.graph_launches += int(self._lib.u1ft_last_host_launch_count())     # host launch calls (graph replay = 1)
         if _advance:
             self.traj_counter += n_traj
         if want_ori:

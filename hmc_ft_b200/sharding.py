@@ -248,6 +248,8 @@ class SlabHMC:
         self._ws = torch.empty(4096 + 24 * (self.Lx + 2), dtype=torch.uint8, device=self._dev)
         self.peers: Optional[PeerRegions] = None
         self.peer_error: Optional[str] = None
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.u1_slab_preload(), "u1_slab_preload")      # no lazy code load behind a spinning kernel
         if self.transport == "peer":
             try:
                 if peers is not None:
@@ -311,6 +313,17 @@ class SlabHMC:
                     return self._replay(g)
         self._eager_calls += 1
         return self._trajectory_body(theta_own, u, self.traj_counter, None)
+
+    def prepare_graph(self, theta_own: torch.Tensor) -> bool:
+        """Capture the trajectory graph now (no replay).  trajectory() does this by itself on its third call; a
+        caller that drives SEVERAL slabs from one process (virtual ranks on one GPU) must capture all of them
+        before replaying any, because torch's capture synchronizes the device and a replay waits for its peers."""
+        if not (self._graph_mode and theta_own.is_cuda):
+            return False
+        key = (theta_own.data_ptr(), tuple(theta_own.shape), torch.cuda.current_stream(self._dev).cuda_stream)
+        if self._graph is None or self._graph["key"] != key:
+            self._capture(theta_own, key)
+        return self._graph is not None
 
     def _replay(self, g) -> Dict[str, torch.Tensor]:
         g["graph"].replay()

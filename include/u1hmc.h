@@ -196,6 +196,10 @@ int u1_peer_alloc(void** dev_ptr, size_t bytes, void* ipc_handle_out);
 int u1_peer_open(const void* ipc_handle, void** dev_ptr);
 int u1_peer_close(void* dev_ptr);
 int u1_peer_free(void* dev_ptr);
+/* Loads the code of every kernel a slab trajectory launches (CUDA loads kernels lazily at first launch, and such
+ * a load may wait for a kernel that is spinning on a peer flag).  Call once per device before the first exchange. */
+int u1_slab_preload(void);
+int u1_plain_preload_slab_kernels(void);
 /* First 8 control words of a region copied to the host (synchronous): [0] top flag, [1] bottom flag,
  * [2] exchange epoch, [5] Metropolis epoch, [6] error word (non-zero: a bounded wait on a peer timed out). */
 int u1_slab_peer_status(const void* region_self, unsigned long long* host_words8);
@@ -250,6 +254,10 @@ size_t u1ft_weight_count(int n_res_blocks);
  * that many sites.  Larger chunks amortise kernel-boundary ramps; the workspace grows linearly.  Returns
  * the previous explicit value (0 = automatic), so passing the return value back restores the behaviour. */
 long long u1ft_set_chunk_sites(long long sites);
+/* u1ft_leapfrog / u1ft_trajectory replay cached CUDA graphs of their building blocks (one FT force + kick, one
+ * forward + action pass; U1FT_GRAPH=0 disables).  u1_last_launch_count() keeps counting KERNELS; this returns the
+ * number of launch API calls the host issued in the last u1ft_* call of this thread (a graph replay counts once). */
+long long u1ft_last_host_launch_count(void);
 /* Workspace for B chains.  with_backward!=0 sizes it for u1ft_force / u1ft_trajectory. */
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward);
 /* field_trans_opt.py:219-243 forward / field_transformation and :284-383 compute_jac_logdet in

@@ -422,4 +422,6 @@ def test_more_than_65535_chains(hb):
     h2 = hb.HMC_U1(L, 2.0, 0, 4, 0.1, device="cuda", if_tune_step_size=False, n_chains=400, seed=5, chain_offset=B - 400)
     b = th[-400:].clone()
     r2 = h2.trajectories(b, 1)
-    assert torch.equal(r["dH"][0, -400:], r2["dH"][0]) and torch.equal(a[-400:], b)
+    # the streaming path's reduction blocking depends on the batch size, so dH agrees to round-off, not bit for bit
+    assert (r["dH"][0, -400:] - r2["dH"][0]).abs().max().item() < 1e-10
+    assert torch.equal(r["accept"][0, -400:], r2["accept"][0]) and torch.equal(a[-400:], b)

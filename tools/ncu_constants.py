@@ -3,11 +3,11 @@ bench.py quotes in its roofline objects (so they are derived from a committed ca
 
     ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum,\\
 dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active \\
-        --clock-control none --csv --log-file gpurun_out/r02_counters.csv python tools/prof_plain.py
+        --clock-control none --csv --log-file gpurun_out/r02_counters.csv python tools/prof_counters.py
     python tools/ncu_constants.py gpurun_out/r02_counters.csv profiles/r02_kernel_constants.json
 
-Kernels are matched by name; counters are averaged over the launches of the same kernel + grid size.  The
-site-updates per launch are fixed by tools/prof_plain.py (C2: 4096 chains x 64^2 sites x 50 steps for
+Kernels are matched by name; the median launch is taken over the launches of the same kernel + grid size.  The
+site-updates per launch are fixed by tools/prof_counters.py (C2: 4096 chains x 64^2 sites x 50 steps for
 k_traj_resident, 4096 x 64^2 for one k_leapfrog_step)."""
 import csv
 import json
@@ -36,16 +36,16 @@ def main(src, dst):
         for name, m in acc.items():
             if key not in name:
                 continue
-            mean = lambda k: (sum(m[k]) / len(m[k])) if m.get(k) else None
+            mean = lambda k: (sorted(m[k])[len(m[k]) // 2]) if m.get(k) else None     # median launch (the thermalisation launch runs 20 trajectories)
             fp64 = mean("sm__inst_executed_pipe_fp64.sum")
-            d = {"kernel": name[:120], "launches_averaged": len(m.get("gpu__time_duration.sum", [])),
+            d = {"kernel": name[:120], "launches_seen": len(m.get("gpu__time_duration.sum", [])),
                  "ncu_time_s_per_launch": mean("gpu__time_duration.sum"),
                  "dram_bytes_per_launch": (mean("dram__bytes_read.sum") or 0) + (mean("dram__bytes_write.sum") or 0),
                  "fp64_warp_inst_per_launch": fp64,
                  "fp64_thread_inst_per_site_update": (fp64 * 32 / su) if fp64 else None,
                  "warp_inst_per_launch": mean("smsp__inst_executed.sum"),
                  "ncu_pipe_fp64_pct": mean("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
-                 "site_updates_per_launch": su, "source": f"{src} (ncu --metrics pass of tools/prof_plain.py, this round)"}
+                 "site_updates_per_launch": su, "source": f"{src} (ncu --metrics pass of tools/prof_counters.py, this round)"}
             out[key] = d
             break
     json.dump(out, open(dst, "w"), indent=1)
