@@ -23,7 +23,7 @@ def main():
     halo = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     transport = sys.argv[3] if len(sys.argv) > 3 else "peer"
     virt = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-    n_traj, n_steps, dt, beta = 6, 9, 0.22, 4.0        # dt large enough that the sample holds accepted and rejected steps
+    n_traj, n_steps, dt, beta = 6, 9, 0.1, 4.0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -31,64 +31,76 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank() if world > 1 else 0
     g = torch.Generator().manual_seed(5)
-    full0 = (torch.rand(2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * 3.0
+    # two starts: near-cold (every step is ACCEPTED, dH << 0: theta evolves through all kernels for 6 trajectories) and
+    # hot (every step is REJECTED, dH >> 0: the select path must leave theta untouched) - checked with the oracle
+    starts = [0.05 * torch.randn(2, L, L, generator=g, dtype=torch.float64),
+              (torch.rand(2, L, L, generator=g, dtype=torch.float64) * 2 - 1) * 3.0]
+    n_phase = [n_traj, 3]
     if virt > 1:
         assert world == 1
         k = max(1, min(halo, L // virt, n_steps))
         regs = PeerRegions.local(virt, k, L)
         slabs = [SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0, transport="peer", peers=regs[r]) for r in range(virt)]
         streams = [torch.cuda.Stream() for _ in range(virt)]
-        owns = [full0[:, r * s.Lx:(r + 1) * s.Lx].contiguous().cuda() for r, s in enumerate(slabs)]
-        torch.cuda.synchronize()
-        outs = [[] for _ in range(virt)]
-        for t in range(n_traj):
-            if t == 2:                                   # all virtual ranks capture before any of them replays
+    else:
+        slabs = [SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0, transport=transport)]
+        streams = [torch.cuda.current_stream()]
+    ranks = [s.rank for s in slabs]
+    Lx = slabs[0].Lx
+    owns = [starts[0][:, rk * Lx:(rk + 1) * Lx].contiguous().cuda() for rk in ranks]
+    ref = hb.HMC_U1(L, beta, 0, n_steps, dt, device="cuda", if_tune_step_size=False, n_chains=1, seed=1331,
+                    kernel_path=1)
+    th = starts[0].cuda()[None].clone()
+    torch.cuda.synchronize()
+    worst, n_acc, t_all = 0.0, 0, 0
+    for phase, (start, nt) in enumerate(zip(starts, n_phase)):
+        if phase > 0:
+            for own, rk in zip(owns, ranks):
+                own.copy_(start[:, rk * Lx:(rk + 1) * Lx])
+            th.copy_(start.cuda()[None])
+            torch.cuda.synchronize()
+        outs = [[] for _ in slabs]
+        for t in range(nt):
+            if t_all == 2 and virt > 1:                  # all virtual ranks capture before any of them replays
                 torch.cuda.synchronize()
                 for r in range(virt):
                     with torch.cuda.stream(streams[r]):
                         assert slabs[r].prepare_graph(owns[r]), slabs[r].graph_error
-            for r in range(virt):
+            for r, slab in enumerate(slabs):
                 with torch.cuda.stream(streams[r]):
-                    outs[r].append(slabs[r].trajectory(owns[r]))
+                    outs[r].append(slab.trajectory(owns[r]))
+            t_all += 1
         torch.cuda.synchronize()
         for s in slabs:
             s.check_peers()
             assert s.graph_error is None, s.graph_error
-    else:
-        slabs = [SlabHMC(L, beta, n_steps, dt, halo=halo, seed=1331, chain=0, transport=transport)]
-        owns = [full0[:, rank * slabs[0].Lx:(rank + 1) * slabs[0].Lx].contiguous().cuda()]
-        outs = [[slabs[0].trajectory(owns[0]) for _ in range(n_traj)]]
-        torch.cuda.synchronize()
-        slabs[0].check_peers()
-        assert slabs[0].graph_error is None, slabs[0].graph_error
-    # reference: the same chain undecomposed
-    ref = hb.HMC_U1(L, beta, 0, n_steps, dt, device="cuda", if_tune_step_size=False, n_chains=1, seed=1331,
-                    kernel_path=1)
-    th = full0.cuda()[None].clone()
-    r = ref.trajectories(th, n_traj)
-    worst = 0.0
-    n_acc = 0
-    for i, (slab, own, out) in enumerate(zip(slabs, owns, outs)):
-        rk = slab.rank
-        for t in range(n_traj):
-            assert abs(out[t]["dH"].item() - r["dH"][t, 0].item()) < 1e-8, (t, out[t]["dH"].item(), r["dH"][t, 0].item())
-            assert int(out[t]["accept"].item()) == int(r["accept"][t, 0].item())
-            assert abs(out[t]["plaq"].item() - r["plaq"][t, 0].item()) < 1e-12
-            assert out[t]["topo"].item() == r["topo"][t, 0].item()
-            n_acc += int(out[t]["accept"].item())
-        want = th[0][:, rk * slab.Lx:(rk + 1) * slab.Lx]
-        err = (own - want).abs().max().item()
-        assert err < 1e-10, err
-        worst = max(worst, err)
-        assert slab.halo.n_exchanges >= n_traj * (2 + (n_steps - 1) // slab.k)
+        r = ref.trajectories(th, nt)                     # the same chain undecomposed (streaming path, one GPU)
+        for slab, own, out in zip(slabs, owns, outs):
+            rk = slab.rank
+            for t in range(nt):
+                assert abs(out[t]["dH"].item() - r["dH"][t, 0].item()) < 1e-8 * max(1.0, abs(r["dH"][t, 0].item())), \
+                    (phase, t, out[t]["dH"].item(), r["dH"][t, 0].item())
+                assert int(out[t]["accept"].item()) == int(r["accept"][t, 0].item())
+                assert abs(out[t]["plaq"].item() - r["plaq"][t, 0].item()) < 1e-12
+                assert out[t]["topo"].item() == r["topo"][t, 0].item()
+                n_acc += int(out[t]["accept"].item())
+            want = th[0][:, rk * Lx:(rk + 1) * Lx]
+            err = (own - want).abs().max().item()
+            assert err < 1e-10, (phase, err)
+            worst = max(worst, err)
+        if phase == 0:
+            assert n_acc == nt * len(slabs), "cold start: every step should be accepted"
+    for slab in slabs:
+        assert slab.halo.n_exchanges >= sum(n_phase) * (2 + (n_steps - 1) // slab.k)
         if slab._graph_mode:
             assert slab._graph is not None, "graph was not captured"
+    assert n_acc == n_phase[0] * len(slabs), "hot start: every step should be rejected"
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print("SLAB_OK world", world, "virtual", virt, "L", L, "halo", slabs[0].k, "transport", slabs[0].transport,
-              "graph", slabs[0]._graph is not None, "max|dtheta|", worst, "accepted", n_acc, "of", n_traj * len(slabs))
+              "graph", slabs[0]._graph is not None, "max|dtheta|", worst, "accepted", n_acc, "of", sum(n_phase) * len(slabs))
 
 
 if __name__ == "__main__":
