@@ -274,6 +274,16 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     kc = kernel_constants()
 
+    if args.slab_only:          # quick sweep mode (U1_SLAB_HALO / U1_MULTISTEP_EW studies): only the configs[4] leg
+        res = bench_slab(args, rank, world, dev, time_steps)
+        if rank == 0:
+            print(json.dumps({"slab_only": True, "n_gpus": world, "env": {k: v for k, v in os.environ.items() if k.startswith("U1_")},
+                              "slab": res}))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
     B = B_PER_GPU
     h = hb.HMC_U1(L, BETA, 0, N_STEPS, DT, device="cuda", if_tune_step_size=False, n_chains=B,
                   chain_offset=rank * B, seed=1331)
@@ -440,6 +450,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-slab", action="store_true")
     ap.add_argument("--no-c1", action="store_true")
+    ap.add_argument("--slab-only", action="store_true")
     ap.add_argument("--ft-cpu-full", action="store_true",
                     help="time 3 full single-chain FT trajectories on the CPU (minutes) instead of the bounded sample")
     args = ap.parse_args()
