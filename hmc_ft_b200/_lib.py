@@ -73,6 +73,11 @@ SIGNATURES = {
     "u1ft_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _sz, _vp]),
     "u1ft_force": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _sz, _vp]),
     "u1ft_leapfrog": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, _vp, _sz, _vp]),
+    "u1ft_train_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "u1_force_hvp": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp]),
+    "u1_loss_grad": (_i, [_vp, _vp, _vp, _d, _sz, _vp, _vp]),
+    "u1ft_train_force_grad": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "u1ft_train_inverse_stage_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _i, _i, _vp, _sz, _vp]),
     "u1ft_trajectory": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _i, _i, _i, _d, _d, _i,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -1732,3 +1732,5 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
 }
 
 }  // extern "C"
+
+#include "u1_ft_train.cuh"

@@ -304,6 +304,32 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
                     double* out_topo, double* theta_ori_out,
                     void* ws, size_t ws_bytes, u1_stream_t stream);
 
+/* ---------------- training gradient of the field transformation (csrc/u1_ft_train.cuh) ----------------
+ * field_trans_opt.py:443-480 train_step = loss_fn -> loss.backward() -> AdamW.  The reference gets d loss / d W from
+ * autograd through the unrolled fixed-point inverse (:245-282) and through compute_force(create_graph=True)
+ * (:400-441); here it is hand-derived.  The caller (hmc_ft_b200/field_trans.py loss_and_grad) composes:
+ *   theta_n = inverse(theta_o), recording each stage's input and iteration count;  d = F_FT(theta_n) - F_plain(theta_n;1)
+ *   v = u1_loss_grad(d);  (Hv, gradW) = u1ft_train_force_grad(theta_n, v);  ubar = Hv - u1_force_hvp(theta_n, v; 1)
+ *   for the stages in reverse order of execution: ubar = u1ft_train_inverse_stage_bwd(stage, ubar)  (+= gradW)
+ * gradW: device [u1ft_weight_count] doubles in the layout of the u1ft_create blob, ACCUMULATED (zero it first). */
+size_t u1ft_train_workspace_bytes(u1ft_handle_t h, int B, int L);
+/* Hessian-vector product of the plain action (hmc_u1.py:56-69 differentiated twice): out = d/d eps force(theta + eps w). */
+int u1_force_hvp(const double* theta, const double* w, double* out, int B, int L, double beta, u1_stream_t stream);
+/* v = d loss / d (a - b) for loss = sum_{p=2,4,6,8} ||a-b||_p / vol^(1/p) (field_trans_opt.py:452-458); sums4 as
+ * produced by u1_diff_power_sums (device). */
+int u1_loss_grad(const double* a, const double* b, const double* sums4, double vol, size_t n, double* v, u1_stream_t stream);
+/* phi = v . F_FT(theta; beta, W):  Hv = d phi / d theta (Hessian-vector product of S_FT), gradW += d phi / d W.
+ * force_check (may be NULL) receives d phi / d v, which must equal u1ft_force(theta) (self check).  phi: reserved, NULL. */
+int u1ft_train_force_grad(u1ft_handle_t h, const double* theta, const double* v, int B, int L, double beta,
+                          double* phi, double* Hv, double* force_check, double* gradW, size_t n_weights,
+                          void* ws, size_t ws_bytes, u1_stream_t stream);
+/* Adjoint of ONE stage of the inverse (subset `index`, n_iter fixed-point iterations from the stage input theta_curr;
+ * n_iter = 0: the stage was skipped): ubar_out = d loss / d theta_curr given ubar_in = d loss / d (stage output);
+ * gradW += contribution of the stage's CNN.  ubar_in != ubar_out. */
+int u1ft_train_inverse_stage_bwd(u1ft_handle_t h, int index, const double* theta_curr, int n_iter, const double* ubar_in,
+                                 double* ubar_out, double* gradW, size_t n_weights, int B, int L,
+                                 void* ws, size_t ws_bytes, u1_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -341,6 +341,33 @@ class FieldTransformationOracle:
             return self.new_force(theta, beta)
         return force_analytic(theta, beta)
 
+    def train_loss_and_grads(self, theta_ori, train_beta: float):
+        """field_trans_opt.py:443-480 (train_step up to the optimizer): loss_fn with autograd through the unrolled
+        fixed-point inverse (:245-282) and through compute_force(create_graph=True) (:400-441), then
+        d loss / d (every CNN weight and bias).  Returns (loss, grads) with grads[subset][layer] = (dW, db) in the
+        layer order of CNNWeights.  Also usable piecewise (see pieces=True) for debugging a device implementation."""
+        params = []
+        for net in self.nets:
+            for i, (w, b) in enumerate(net.layers):
+                w = w.detach().clone().requires_grad_(True)
+                b = b.detach().clone().requires_grad_(True)
+                net.layers[i] = (w, b)
+                params += [w, b]
+        th_new, _ = self.inverse(theta_ori)
+        t = th_new if th_new.requires_grad else th_new.clone().requires_grad_(True)
+        f_ori = torch.autograd.grad(action(t, 1.0).sum(), t, create_graph=True)[0]
+        f_new = torch.autograd.grad(self.new_action(t, train_beta).sum(), t, create_graph=True)[0]
+        vol = float(self.L * self.L)
+        d = f_new - f_ori
+        loss = sum(torch.norm(d, p=p) / vol ** (1.0 / p) for p in (2, 4, 6, 8))
+        g = torch.autograd.grad(loss, params, allow_unused=True)
+        grads, it = [], iter(g)
+        for net in self.nets:
+            grads.append([(next(it), next(it)) for _ in net.layers])
+        for net in self.nets:                      # leave the oracle with plain tensors again
+            net.layers = [(w.detach(), b.detach()) for w, b in net.layers]
+        return loss.detach(), grads
+
     def loss_fn(self, theta_ori, train_beta: float):
         """field_trans_opt.py:443-462: theta_new = inverse(theta_ori); the four p-norms (p = 2,4,6,8, taken over
         the WHOLE batch tensor) of F_FT(theta_new; train_beta) - F_plain(theta_new; beta=1), each divided by

@@ -196,3 +196,22 @@ def test_tune_step_size_matches_reference(golden_dir):
         assert abs(dt - dt_ref) < 1e-6                       # the reference prints 6 decimals
         assert round(rate * int(n_tune)) == round(float(rate_ref) * int(n_tune))
     assert h.dt == float(z["tuned_dt"])
+
+
+@pytest.mark.parametrize("tag", ["rnet3_L8", "simple_L16"])
+def test_training_gradient_matches_reference(golden_dir, tag):
+    """field_trans_opt.py:443-480: loss and d loss / d weights of the oracle's autograd restatement against the REAL
+    reference's train_step (tools/gen_golden_train.py): loss to 1e-12, every gradient tensor to 1e-9 of the largest
+    gradient entry (double backward through ~10 unrolled inverse iterations per subset)."""
+    z = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    arch, L = str(z["arch"]), int(z["L"])
+    keys = O.STATE_KEYS[arch]
+    sds = [{f"{k}.{wb}": z[f"w{s}.{k}.{wb}"] for k in keys for wb in ("weight", "bias")} for s in range(8)]
+    fo = O.FieldTransformationOracle(L, O.weights_from_state_dicts(arch, sds))
+    loss, grads = fo.train_loss_and_grads(T(z["theta_ori"]), float(z["train_beta"]))
+    assert abs(loss.item() - float(z["loss"])) < 1e-12 * abs(float(z["loss"]))
+    gmax = max(np.abs(z[f"g{s}.{k}.weight"]).max() for s in range(8) for k in keys)
+    for s in range(8):
+        for li, k in enumerate(keys):
+            assert np.abs(grads[s][li][0].numpy() - z[f"g{s}.{k}.weight"]).max() < 1e-9 * gmax
+            assert np.abs(grads[s][li][1].numpy() - z[f"g{s}.{k}.bias"]).max() < 1e-9 * gmax
