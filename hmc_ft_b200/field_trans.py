@@ -1,7 +1,6 @@
-"""FieldTransformation (2d_u1_cluster/field_trans_opt.py:26-505,654-692) on the sm_100a library: forward,
-log-det, inverse, S_FT and its force, and the VALUE of the training loss (loss_fn / evaluate_step).
-Training itself (gradient of the loss with respect to the CNN weights, train_step / train) is out of scope
-(SURVEY §8f.4)."""
+"""FieldTransformation (2d_u1_cluster/field_trans_opt.py:26-692) on the sm_100a library: forward, log-det,
+inverse, S_FT and its force, the training loss (loss_fn / evaluate_step) and its hand-derived gradient with respect
+to the CNN weights (loss_and_grad -> train_step / train with AdamW on the host), checkpoint save / load."""
 from __future__ import annotations
 
 import ctypes as C
@@ -194,7 +193,7 @@ class FieldTransformation:
         self._count()
         return K
 
-    def inverse(self, theta, max_iter: int = 200, tol: float = 1e-6):
+    def inverse(self, theta, max_iter: int = 200, tol: float = 1e-6, _trace=None):
         """field_trans_opt.py:245-282: theta_ori -> theta_new by per-subset fixed-point iteration, same
         stopping rule (global relative change < tol, tested on the host every iteration; a subset
         that does not converge within max_iter is left unchanged, with a warning).  The subset's
@@ -210,6 +209,7 @@ class FieldTransformation:
             for index in reversed(range(self.n_subsets)):
                 K = self._coefficients(cur, index)
                 it.copy_(cur)
+                stage_in = cur.clone() if _trace is not None else None
                 diff, n_it = float("inf"), 0
                 for i in range(max_iter):
                     _lib.check(self._lib.u1ft_inverse_iter(cur.data_ptr(), it.data_ptr(), K.data_ptr(), index,
@@ -226,6 +226,8 @@ class FieldTransformation:
                 if not diff < tol:
                     self.print(f"Warning: Inverse iteration for subset {index} did not converge, final diff = {diff:.2e}")
                 self.inverse_iterations.append(n_it)
+                if _trace is not None:      # (subset, stage input, iterations; 0 = not converged, stage skipped)
+                    _trace.append((index, stage_in, n_it if diff < tol else 0))
         return self._back(cur, theta, single)
 
     def inverse_field_transformation(self, theta):
@@ -342,10 +344,122 @@ class FieldTransformation:
         """field_trans_opt.py:490-505: loss of one evaluation batch as a Python float."""
         return float(self.loss_fn(theta_ori).item())
 
-    def train_step(self, theta_ori):
-        raise NotImplementedError("CNN training (double backward through the FT force) is outside the sampling hot path; "
-                                  "train with the reference and load the checkpoint (load_checkpoint / _load_best_model)")
+    # ------------------------------------------------------------------ training (field_trans_opt.py:443-652)
+    def loss_and_grad(self, theta_ori, train_beta: Optional[float] = None, check: bool = False):
+        """loss_fn (field_trans_opt.py:443-462) and its gradient with respect to every CNN weight, hand-derived on the
+        device (csrc/u1_ft_train.cuh) - what the reference obtains from loss.backward() through the unrolled
+        fixed-point inverse and compute_force(create_graph=True).  Returns (loss, gradW): a 0-dim fp64 device tensor
+        and a flat fp64 device tensor in the layout of the weight blob (per subset, per conv layer: W[o][c][3][3], b[o])."""
+        beta = self.train_beta if train_beta is None else train_beta
+        if beta is None:
+            raise ValueError("loss_and_grad needs train_beta (set .train_beta or pass train_beta=)")
+        beta = float(beta)
+        lib, dev, L = self._lib, self._dev, self.L
+        trace = []
+        th_new = self.inverse(theta_ori, _trace=trace)
+        d_new, _, B = self._stage(th_new)
+        d_new = d_new.contiguous()
+        f_ori = self.compute_force(d_new, 1.0)
+        f_new = self.new_force(d_new, beta)
+        n = f_new.numel()
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        v = torch.empty_like(f_new)
+        n_w = int(lib.u1ft_weight_count(self.models[0].n_res_blocks))
+        gradW = torch.zeros(n_w, dtype=torch.float64, device=dev)
+        Hv, Hp = torch.empty_like(f_new), torch.empty_like(f_new)
+        fchk = torch.empty_like(f_new) if check else None
+        vol = float(L * L)
+        with torch.cuda.device(dev):
+            sp = stream_ptr(dev)
+            ws, nb = WS.get(dev, lib.u1_diff_power_sums_workspace_bytes(), "loss")
+            _lib.check(lib.u1_diff_power_sums(f_new.data_ptr(), f_ori.data_ptr(), n, sums.data_ptr(), ws, nb, sp), "u1_diff_power_sums")
+            _lib.check(lib.u1_loss_grad(f_new.data_ptr(), f_ori.data_ptr(), sums.data_ptr(), vol, n, v.data_ptr(), sp), "u1_loss_grad")
+            tws, tnb = WS.get(dev, lib.u1ft_train_workspace_bytes(self._handle, B, L), "fttrain")
+            # (1) d/dW [v . F_FT(theta_n)] and the Hessian-vector product H_FT v
+            _lib.check(lib.u1ft_train_force_grad(self._handle, d_new.data_ptr(), v.data_ptr(), B, L, beta, None, Hv.data_ptr(),
+                                                 None if fchk is None else fchk.data_ptr(), gradW.data_ptr(), n_w, tws, tnb, sp),
+                       "u1ft_train_force_grad")
+            self._count()
+            _lib.check(lib.u1_force_hvp(d_new.data_ptr(), v.data_ptr(), Hp.data_ptr(), B, L, 1.0, sp), "u1_force_hvp")
+            ubar = Hv - Hp                                   # d loss / d theta_n
+            # (2) through the inverse: stages in reverse order of execution (the inverse ran subsets 7..0)
+            for index, stage_in, n_it in reversed(trace):
+                nxt = torch.empty_like(ubar)
+                _lib.check(lib.u1ft_train_inverse_stage_bwd(self._handle, int(index), stage_in.data_ptr(), int(n_it),
+                                                            ubar.data_ptr(), nxt.data_ptr(), gradW.data_ptr(), n_w, B, L,
+                                                            tws, tnb, sp), "u1ft_train_inverse_stage_bwd")
+                self._count()
+                ubar = nxt
+        p = torch.tensor([2.0, 4.0, 6.0, 8.0], dtype=torch.float64, device=dev)
+        loss = (sums.pow(1.0 / p) / vol ** (1.0 / p)).sum()
+        if check:       # d(v . F_FT)/dv must reproduce the force: catches a broken reverse sweep without any reference
+            self.last_force_check = float((fchk - f_new).abs().max().item() / max(f_new.abs().max().item(), 1e-300))
+        self.last_theta_ori_grad = ubar
+        return loss, gradW
 
-    def train(self, *args, **kwargs):
-        return self.train_step(None)
+    def _ensure_optimizers(self):
+        """field_trans_opt.py:53-70: one AdamW(lr=1e-3, weight_decay=1e-4) and one ReduceLROnPlateau(0.5, patience 5) per
+        subset model (host-side torch.optim on the parameter containers: bookkeeping, not the hot path)."""
+        if getattr(self, "optimizers", None) is None:
+            self.optimizers = [torch.optim.AdamW(m.parameters(), lr=0.001, weight_decay=1e-4) for m in self.models]
+            self.schedulers = [torch.optim.lr_scheduler.ReduceLROnPlateau(o, mode="min", factor=0.5, patience=5)
+                               for o in self.optimizers]
+
+    def _assign_grads(self, gradW: torch.Tensor) -> None:
+        g = gradW.detach().to("cpu")
+        off = 0
+        for m in self.models:
+            for c in m.conv_layers():
+                for prm in (c.weight, c.bias):
+                    k = prm.numel()
+                    prm.grad = g[off:off + k].reshape(prm.shape).to(prm.dtype).clone()
+                    off += k
+        assert off == g.numel()
+
+    def train_step(self, theta_ori):
+        """field_trans_opt.py:463-480: loss -> gradients -> one AdamW step of all 8 subset models -> new device handle."""
+        self._ensure_optimizers()
+        loss, gradW = self.loss_and_grad(theta_ori)
+        for o in self.optimizers:
+            o.zero_grad()
+        self._assign_grads(gradW)
+        for o in self.optimizers:
+            o.step()
+        self.sync_weights()
+        return float(loss.item())
+
+    def _save_best_model(self, epoch, loss):
+        """field_trans_opt.py:619-640: the reference's checkpoint format (loadable by both code bases)."""
+        d = {"epoch": epoch, "loss": loss}
+        for i, m in enumerate(self.models):
+            d[f"model_state_dict_{i}"] = m.state_dict()
+        for i, o in enumerate(self.optimizers):
+            d[f"optimizer_state_dict_{i}"] = o.state_dict()
+        os.makedirs("models", exist_ok=True)
+        tag = "" if self.save_tag is None else f"_{self.save_tag}"
+        torch.save(d, f"models/best_model_opt_L{self.L}_train_beta{self.train_beta:.1f}{tag}.pt")
+
+    def train(self, train_data, test_data, train_beta, n_epochs=100, batch_size=4):
+        """field_trans_opt.py:507-584: epochs of train_step over the training set, evaluate_step over the test set,
+        best checkpoint kept, ReduceLROnPlateau on the test loss; the best model is re-loaded at the end.  Returns
+        (train_losses, test_losses) (the reference plots them; matplotlib is optional here)."""
+        self.train_beta = float(train_beta)
+        self._ensure_optimizers()
+        tr = torch.utils.data.DataLoader(train_data, batch_size=batch_size, shuffle=True, num_workers=self.num_workers)
+        te = torch.utils.data.DataLoader(test_data, batch_size=batch_size, num_workers=self.num_workers)
+        train_losses, test_losses, best = [], [], float("inf")
+        self.print(f"\n>>> Training the model at beta = {train_beta}\n")
+        for epoch in range(n_epochs):
+            ep = [self.train_step(b) for b in tr]
+            train_losses.append(float(np.mean(ep)))
+            ev = [self.evaluate_step(b) for b in te]
+            test_losses.append(float(np.mean(ev)))
+            self.print(f"Epoch {epoch + 1}/{n_epochs} - Train Loss: {train_losses[-1]:.6f} - Test Loss: {test_losses[-1]:.6f}")
+            if test_losses[-1] < best:
+                self._save_best_model(epoch, test_losses[-1])
+                best = test_losses[-1]
+            for sch in self.schedulers:
+                sch.step(test_losses[-1])
+        self._load_best_model(self.train_beta)
+        return train_losses, test_losses
 
