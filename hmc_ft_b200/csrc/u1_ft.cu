@@ -263,8 +263,10 @@ constexpr int kTileStages = 3;
 #define U1_TAB_CPASYNC 1
 #endif
 
+// ROWS < 4 (small batches, see tile_rows_for) needs the tighter register cap: at 128 registers ptxas schedules that
+// body ~30 % slower (round-1 measurement).
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))
+__global__ void __launch_bounds__(kConvThreads, (ROWS < 4 ? 6 : (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB)))
 k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
             const double* __restrict__ add, const double* __restrict__ mul,
             double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
@@ -1060,10 +1062,9 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int b
     cfg.numAttrs = 1;
 }
 
-template <int LL, int CIN, int COUT, int EPI>
+template <int LL, int ROWS, int CIN, int COUT, int EPI>
 static int launch_conv_tile(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                             const double* mul, double* out, double* dout, int nsites, cudaStream_t st) {
-    constexpr int ROWS = (EPI == EPI_BWD) ? 4 : U1_TILE_FWD_ROWS;
     constexpr int TILE = (ROWS * (kConvThreads / LL) + 2) * LL;
     constexpr size_t smem = ((size_t)kTileStages * TILE + (EPI == EPI_BWD ? 0 : kGeluTableDoubles)) * sizeof(double);
     static std::atomic<bool> configured[kMaxDevices];      // function attributes are per device
@@ -1088,15 +1089,35 @@ static int tile_path_enabled() {          // U1FT_TILE: 0 off, 1 reverse layers 
     return v;
 }
 
+// Lattice rows per thread of the tiled convolution.  4 rows (four DFMAs per constant-bank weight read) is the
+// fastest body, but a layer then has only nsites/512 CTAs of 4 warps: at 128 chains of L=32 that is 256 CTAs
+// for 148 SMs x 4 resident CTAs, i.e. under two warps per scheduler and nothing to hide the LDS / barrier
+// latency of the channel loop.  Small launches therefore trade per-thread reuse for parallelism
+// (2 or 1 rows per thread).  U1FT_TILE_ROWS=1|2|4 forces a value.
+static int tile_rows_for(int nsites) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("U1FT_TILE_ROWS"); forced = e ? atoi(e) : 0; }
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    static int t4 = -1, t2 = -1;                      // thresholds in CTAs of the ROWS=4 launch (tunable)
+    if (t4 < 0) { const char* e = getenv("U1FT_TILE_T4"); t4 = e ? atoi(e) : 600; }
+    if (t2 < 0) { const char* e = getenv("U1FT_TILE_T2"); t2 = e ? atoi(e) : 300; }
+    const int ctas4 = nsites / (4 * kConvThreads);
+    return ctas4 >= t4 ? 4 : (ctas4 >= t2 ? 2 : 1);
+}
+
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
     // Measured in the full force (342 chains): reverse layers 135 vs 161 us (ncu), forward layers 161 vs 228 us
     // against the direct kernel; the register caps of the tiled kernels are the U1_TILE_*_MINB knobs above.
-    if (tile_path_enabled() && (EPI == EPI_BWD || tile_path_enabled() > 1)) {
-        if (L == 64) return launch_conv_tile<64, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
-        if (L == 32) return launch_conv_tile<32, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
-        if (L == 128) return launch_conv_tile<128, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+    if (tile_path_enabled() && (EPI == EPI_BWD || tile_path_enabled() > 1) && (L == 32 || L == 64 || L == 128)) {
+        const int rows = tile_rows_for(nsites);
+#define U1_TILE_CASE(LLv, Rv) \
+        if (L == LLv && rows == Rv) return launch_conv_tile<LLv, Rv, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+        U1_TILE_CASE(64, 4) U1_TILE_CASE(64, 2) U1_TILE_CASE(64, 1)
+        U1_TILE_CASE(32, 4) U1_TILE_CASE(32, 2) U1_TILE_CASE(32, 1)
+        U1_TILE_CASE(128, 4) U1_TILE_CASE(128, 2) U1_TILE_CASE(128, 1)
+#undef U1_TILE_CASE
     }
     const int npairs = nsites >> 1;
     const size_t smem = (EPI == EPI_BWD) ? 0 : (size_t)kGeluTableDoubles * sizeof(double);
