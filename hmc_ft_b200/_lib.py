@@ -34,6 +34,8 @@ SIGNATURES = {
     "u1_slab_leapfrog_step": (_i, [_vp] * 8 + [_i, _i, _d, _d, _d, _vp]),
     "u1_leapfrog_step_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _vp]),
     "u1_leapfrog_steps_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _i, C.POINTER(_i), _vp]),
+    "u1_leapfrog_multi_tile_rows": (_i, [_i]),
+    "u1_leapfrog_multi_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _i, _vp]),
     "u1_momenta_rows": (_i, [_vp, _u64, _u64, _u64, C.c_longlong, _i, _i, _i, _vp]),
     "u1_momenta_rows_dev": (_i, [_vp, _u64, _u64, _u64, _vp, C.c_longlong, _i, _i, _i, _vp]),
     "u1_drift_wrap": (_i, [_vp, _vp, _vp, _d, _sz, _vp]),

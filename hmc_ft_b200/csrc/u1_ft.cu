@@ -1093,14 +1093,17 @@ static int tile_path_enabled() {          // U1FT_TILE: 0 off, 1 reverse layers 
 // fastest body, but a layer then has only nsites/512 CTAs of 4 warps: at 128 chains of L=32 that is 256 CTAs
 // for 148 SMs x 4 resident CTAs, i.e. under two warps per scheduler and nothing to hide the LDS / barrier
 // latency of the channel loop.  Small launches therefore trade per-thread reuse for parallelism
-// (2 or 1 rows per thread).  U1FT_TILE_ROWS=1|2|4 forces a value.
+// (2 rows per thread).  Measured on one B200 at the per-GPU batch of the 8-GPU run (profiles/r02_ft_small_batch_rows.log,
+// rnet3, 128 chains): L=32 (256 CTAs at 4 rows): 710 -> 767 trajectories/s with 2 rows, 397 with 1 row; L=64 (1024
+// CTAs): 348 / 338 / 119; L=32 with 256 chains (512 CTAs): 1156 -> 1234.  Hence 2 rows below 600 CTAs, never 1.
+// U1FT_TILE_ROWS=1|2|4 forces a value.
 static int tile_rows_for(int nsites) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("U1FT_TILE_ROWS"); forced = e ? atoi(e) : 0; }
     if (forced == 1 || forced == 2 || forced == 4) return forced;
     static int t4 = -1, t2 = -1;                      // thresholds in CTAs of the ROWS=4 launch (tunable)
     if (t4 < 0) { const char* e = getenv("U1FT_TILE_T4"); t4 = e ? atoi(e) : 600; }
-    if (t2 < 0) { const char* e = getenv("U1FT_TILE_T2"); t2 = e ? atoi(e) : 300; }
+    if (t2 < 0) { const char* e = getenv("U1FT_TILE_T2"); t2 = e ? atoi(e) : 0; }
     const int ctas4 = nsites / (4 * kConvThreads);
     return ctas4 >= t4 ? 4 : (ctas4 >= t2 ? 2 : 1);
 }

@@ -276,6 +276,7 @@ struct MultiArgs {
     const double* th; const double* pi;
     double* tho; double* pio;
     int Lx, L, tiles_y, ksteps;
+    int tile_x0;          // first tile row of this launch (launches may cover a sub-range of tile rows)
     double beta, first_drift, dt;
 };
 
@@ -294,7 +295,8 @@ k_leapfrog_multi(MultiArgs a) {
     const int x0 = tx * TX, y0 = ty * TY;
     const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
     const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
-    const int tile_x = blockIdx.x / a.tiles_y, tile_y = blockIdx.x - tile_x * a.tiles_y;
+    const int tile_xl = blockIdx.x / a.tiles_y, tile_y = blockIdx.x - tile_xl * a.tiles_y;
+    const int tile_x = a.tile_x0 + tile_xl;
     const size_t V = (size_t)a.Lx * a.L;
     const size_t base = (size_t)blockIdx.y * 2 * V;
     // global coordinates of this thread's 2 x 4 sites (periodic)
@@ -396,13 +398,18 @@ static bool multi_supported(int Lx, int L) {
 }
 
 static int launch_multi(const double* th, const double* pi, double* tho, double* pio, int B, int Lx, int L,
-                        double beta, double first_drift, double dt, int ksteps, cudaStream_t st) {
+                        double beta, double first_drift, double dt, int ksteps, cudaStream_t st,
+                        int tile_row0 = 0, int tile_rows = -1) {
     MultiArgs a{};
     a.th = th; a.pi = pi; a.tho = tho; a.pio = pio;
     a.Lx = Lx; a.L = L; a.ksteps = ksteps; a.beta = beta; a.first_drift = first_drift; a.dt = dt;
     static int ew = 0;
     if (ew == 0) { const char* e = getenv("U1_MULTISTEP_EW"); ew = (e && atoi(e) == 64) ? 64 : 32; }
-    const int tiles_x = (Lx + kMsOut - 1) / kMsOut;
+    const int tiles_all = (Lx + kMsOut - 1) / kMsOut;
+    if (tile_rows < 0) tile_rows = tiles_all - tile_row0;
+    if (tile_row0 < 0 || tile_rows < 1 || tile_row0 + tile_rows > tiles_all) return U1_ERR_ARG;
+    a.tile_x0 = tile_row0;
+    const int tiles_x = tile_rows;
     constexpr int NTX = kMsE / 2;
     if (ew == 64) {
         constexpr int NTY = 16;
@@ -1216,6 +1223,20 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
                               (cudaStream_t)stream, &ct, &cp));
     *result_in_B = (ct == thetaB) ? 1 : 0;
     return U1_OK;
+}
+
+int u1_leapfrog_multi_tile_rows(int Lx) { return Lx > 0 ? (Lx + kMsOut - 1) / kMsOut : 0; }
+
+int u1_leapfrog_multi_rows(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                           int Lx, int L, double beta, double first_drift, double dt, int ksteps,
+                           int tile_row0, int tile_rows, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || Lx <= 0 || L <= 0) return U1_ERR_ARG;
+    if (theta_in == theta_out || pi_in == pi_out || ksteps < 1 || ksteps > kMsHalo) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(theta_out) || !aligned16(pi_out)) return U1_ERR_ARG;
+    if (!multi_supported(Lx, L)) return U1_ERR_UNSUPPORTED;
+    return launch_multi(theta_in, pi_in, theta_out, pi_out, 1, Lx, L, beta, first_drift, dt, ksteps, (cudaStream_t)stream,
+                        tile_row0, tile_rows);
 }
 
 int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,

@@ -225,10 +225,8 @@ class SlabHMC:
         if self.transport not in ("peer", "nccl"):
             raise ValueError("transport must be 'peer' or 'nccl'")
         if halo is None:
-            # peer: an exchange is one ~10-20 us kernel, so few redundant rows win (2k/Lx extra compute, one
-            # exchange per k steps); nccl: host-driven send/recv per exchange, so fewer, larger exchanges
             env = os.environ.get("U1_SLAB_HALO")
-            halo = int(env) if env else (16 if self.transport == "peer" else max(10, self.Lx // 16))
+            halo = int(env) if env else (self._choose_halo() if self.transport == "peer" else max(10, self.Lx // 16))
         self.k = max(1, min(int(halo), self.Lx, self.n_steps))
         self.x0 = self.rank * self.Lx
         self.seed, self.chain = int(seed), int(chain)
@@ -268,6 +266,33 @@ class SlabHMC:
         self._graph = None
         self._eager_calls = 0
         self.graph_error: Optional[str] = None
+        # peer transport: exchanges run on a side stream while the main stream advances the tile rows that do not
+        # touch halo rows (U1_SLAB_OVERLAP=0: everything on one stream)
+        self._overlap = self.transport == "peer" and os.environ.get("U1_SLAB_OVERLAP", "1") == "1"
+        self._side = torch.cuda.Stream(device=self._dev) if self._overlap else None
+        Lxe = self.Lx + 2 * self.k
+        T = int(self._lib.u1_leapfrog_multi_tile_rows(Lxe))
+        inner = [i for i in range(T) if 56 * i - 4 >= self.k and 56 * i + 60 <= self.Lx + self.k]
+        multi_ok = self.L % 4 == 0 and Lxe >= 64 and self.L >= 64 and os.environ.get("U1_MULTISTEP", "1") != "0"
+        # tile rows [i0, i1) read no halo row; [0, i0) and [i1, T) wait for the exchange
+        self._split = (inner[0], inner[-1] + 1, T) if (self._overlap and multi_ok and len(inner) >= 2) else None
+
+    def _choose_halo(self) -> int:
+        """Halo width for the peer transport from a two-term cost model fitted to the 8-GPU sweep of round 2
+        (profiles/r02_slab_8gpu_halo_sweep.json): the temporally blocked kernel works on whole 56-row tile rows, so a
+        trajectory costs (launches) x ceil((Lx + 2k)/56) tile rows, plus ~2 tile-row-launches worth of time per exchange
+        (an exchange is one ~10 us push/unpack kernel).  Multiples of 4 (steps per launch) only."""
+        best, best_cost = 4, float("inf")
+        for k in range(4, 33, 4):
+            if k > self.Lx or k > max(4, self.n_steps):
+                break
+            blocks = [min(k, self.n_steps - d) for d in range(0, self.n_steps, k)]
+            launches = sum(-(-b // 4) for b in blocks)
+            tile_rows = -(-(self.Lx + 2 * k) // 56)
+            cost = launches * tile_rows + 2.0 * (len(blocks) + 1)
+            if cost < best_cost - 1e-9:
+                best, best_cost = k, cost
+        return best
 
     def initialize(self) -> torch.Tensor:
         return torch.zeros(2, self.Lx, self.L, dtype=torch.float64, device=self._dev)
@@ -385,24 +410,51 @@ class SlabHMC:
             sp = stream_ptr(dev)
             ws, nb = self._ws.data_ptr(), self._ws.numel()
             self._call(lib.u1_slab_copy_in(theta_own.data_ptr(), cur[0, 0, k].data_ptr(), plane, Lx, L, sp), "u1_slab_copy_in")
+            # theta halo exchange on the side stream, concurrent with the momenta kernel (it only writes pi)
+            main = torch.cuda.current_stream(dev)
+            side = self._side if self._overlap else None
+            if side is not None:
+                side.wait_stream(main)
+                self._exchange(cur, False, k, k, side.cuda_stream)
             # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
             self._call(lib.u1_momenta_rows_dev(cur[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
                                                Lx + 2 * k, L, L, sp), "u1_momenta_rows")
-            self._exchange(cur, False, k, k, sp)             # theta halos
+            if side is not None:
+                main.wait_stream(side)
+            else:
+                self._exchange(cur, False, k, k, sp)         # theta halos
             self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
                                             s6[0:3].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
             done = 0
             while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
-                if done > 0:
-                    self._exchange(cur, True, k, k, sp)      # theta and pi, k rows each side
                 nblk = min(k, self.n_steps - done)
-                in_b = C.c_int(0)
-                self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
-                                                      nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
-                                                      0.5 * dt if done == 0 else dt, dt, nblk, C.byref(in_b), sp),
-                           "u1_leapfrog_steps_rect")
-                if in_b.value:
+                first = 0                                    # steps of this block already taken by the split launch
+                if done > 0 and self._split is not None:
+                    # (theta, pi) exchange on the side stream; meanwhile the first <= 4 steps of the interior tile
+                    # rows (their 64-row windows read no halo row), then the boundary tile rows once the halos are in
+                    i0, i1, T = self._split
+                    first = min(4, nblk)
+                    side.wait_stream(main)
+                    self._exchange(cur, True, k, k, side.cuda_stream)
+                    args = (cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(), nxt[1].data_ptr(), Lx + 2 * k, L,
+                            self.beta, dt, dt, first)
+                    self._call(lib.u1_leapfrog_multi_rows(*args, i0, i1 - i0, sp), "u1_leapfrog_multi_rows")
+                    main.wait_stream(side)
+                    if i0 > 0:
+                        self._call(lib.u1_leapfrog_multi_rows(*args, 0, i0, sp), "u1_leapfrog_multi_rows")
+                    if T > i1:
+                        self._call(lib.u1_leapfrog_multi_rows(*args, i1, T - i1, sp), "u1_leapfrog_multi_rows")
                     cur, nxt = nxt, cur
+                elif done > 0:
+                    self._exchange(cur, True, k, k, sp)      # theta and pi, k rows each side
+                if nblk > first:
+                    in_b = C.c_int(0)
+                    self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
+                                                          nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
+                                                          0.5 * dt if done == 0 else dt, dt, nblk - first, C.byref(in_b), sp),
+                               "u1_leapfrog_steps_rect")
+                    if in_b.value:
+                        cur, nxt = nxt, cur
                 done += nblk
             # final half drift + wrap on own rows, in place (hmc_u1.py:78-79), then H_new
             self._call(lib.u1_slab_drift_wrap(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane, Lx, L, 0.5 * dt, sp),

@@ -139,6 +139,15 @@ int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* t
 int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
                            int B, int Lx, int L, double beta, double first_drift, double dt, int n,
                            int* result_in_B, u1_stream_t stream);
+/* One launch of the temporally blocked kernel restricted to tile rows [tile_row0, tile_row0 + tile_rows) of the
+ * u1_leapfrog_multi_tile_rows(Lx) rows of 56-row tiles: ksteps <= 4 leapfrog steps (first drift first_drift, then
+ * dt) from (theta_in, pi_in) to (theta_out, pi_out); a tile row reads rows [56 i - 4, 56 i + 60) (periodic) and
+ * writes rows [56 i, 56 i + 56).  Lets the slab path advance the interior of a slab while the halo exchange is
+ * still in flight and finish the boundary tile rows afterwards.  U1_ERR_UNSUPPORTED unless L % 4 == 0, Lx, L >= 64. */
+int u1_leapfrog_multi_tile_rows(int Lx);
+int u1_leapfrog_multi_rows(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                           int Lx, int L, double beta, double first_drift, double dt, int ksteps,
+                           int tile_row0, int tile_rows, u1_stream_t stream);
 /* Philox momenta for rows x_first .. x_first+Lx-1 (taken modulo Lx_global) of ONE global lattice of
  * Lx_global x L sites: pi[2][Lx][L].  Keyed by the global site index, so the field does not depend
  * on the decomposition. */

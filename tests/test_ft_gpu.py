@@ -297,5 +297,4 @@ def test_training_loss_value(golden_dir, tag, wfile):
     _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
     want = O.FieldTransformationOracle(L, nets).loss_fn(torch.tensor(z["theta_ori"]), beta).item()
     assert abs(ft.loss_fn(torch.tensor(z["theta_ori"]), train_beta=beta).item() - want) < 1e-9 * abs(want)
-    with pytest.raises(NotImplementedError):
-        ft.train_step(torch.tensor(z["theta_ori"]))
+    # train_step itself: tests/test_train_gpu.py
