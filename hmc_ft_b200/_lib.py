@@ -34,6 +34,8 @@ SIGNATURES = {
     "u1_slab_leapfrog_step": (_i, [_vp] * 8 + [_i, _i, _d, _d, _d, _vp]),
     "u1_leapfrog_step_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _vp]),
     "u1_leapfrog_steps_rect": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _i, C.POINTER(_i), _vp]),
+    "u1_leapfrog_steps_rect3": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _i, C.POINTER(_i), _vp]),
+    "u1_slab_drift_sums_ext": (_i, [_vp, _vp, _sz, _vp, _d, _vp, _i, _i, _vp, _sz, _vp]),
     "u1_leapfrog_multi_tile_rows": (_i, [_i]),
     "u1_leapfrog_multi_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _i, _vp]),
     "u1_momenta_rows": (_i, [_vp, _u64, _u64, _u64, C.c_longlong, _i, _i, _i, _vp]),
@@ -58,6 +60,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "u1_slab_drift_wrap": (_i, [_vp, _vp, _sz, _i, _i, _d, _vp]),
     "u1_slab_copy_in": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "u1_slab_select_state": (_i, [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp]),
     "u1_slab_select": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
     "u1_diff_power_sums_workspace_bytes": (C.c_size_t, []),
     "u1_diff_power_sums": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp]),

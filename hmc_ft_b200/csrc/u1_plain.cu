@@ -280,6 +280,11 @@ struct MultiArgs {
     double beta, first_drift, dt;
 };
 
+// Measured and rejected in round 2 (profiles/r02_multistep_prefetch_variants.log): a persistent form (2 CTAs per SM
+// walking windows) that asks L2 for the CTA's next window right after a window sits in registers, with
+// cp.async.bulk.prefetch.L2 (SASS UBLKPF.L2) or per-line prefetch.global.L2 (CCTL.E.PF2): bit-identical, but 338 / 332 us
+// per 4 steps at L=4096 against 307 us for one window per CTA - the hardware CTA scheduler overlaps the load phase of
+// a fresh CTA with its neighbour's steps better than the in-kernel loop does.
 template <int EW>      // window columns (64: one 512-thread CTA per SM; 32: two 256-thread CTAs per SM overlap their phases)
 __global__ void __launch_bounds__((kMsE / 2) * (EW / 4), 512 / ((kMsE / 2) * (EW / 4)))
 k_leapfrog_multi(MultiArgs a) {
@@ -295,9 +300,10 @@ k_leapfrog_multi(MultiArgs a) {
     const int x0 = tx * TX, y0 = ty * TY;
     const int tyR = (ty + 1) % NTY, tyL = (ty + NTY - 1) % NTY;
     const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
+    const size_t V = (size_t)a.Lx * a.L;
+    const double kb = a.dt * a.beta;
     const int tile_xl = blockIdx.x / a.tiles_y, tile_y = blockIdx.x - tile_xl * a.tiles_y;
     const int tile_x = a.tile_x0 + tile_xl;
-    const size_t V = (size_t)a.Lx * a.L;
     const size_t base = (size_t)blockIdx.y * 2 * V;
     // global coordinates of this thread's 2 x 4 sites (periodic)
     int gy = tile_y * OW - kMsHalo + y0;
@@ -319,7 +325,6 @@ k_leapfrog_multi(MultiArgs a) {
             th0[i][j] = v0.x; th0[i][j + 1] = v0.y; th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
             p0[i][j] = q0.x; p0[i][j + 1] = q0.y; p1[i][j] = q1.x; p1[i][j + 1] = q1.y;
         }
-    const double kb = a.dt * a.beta;
     for (int s = 0; s < a.ksteps; ++s) {
         const double dr = (s == 0) ? a.first_drift : a.dt;
 #pragma unroll
@@ -389,6 +394,18 @@ k_leapfrog_multi(MultiArgs a) {
             *reinterpret_cast<double2*>(a.pio + g + V) = make_double2(p1[i][j], p1[i][j + 1]);
         }
     }
+}
+
+// SM count of the current device (cached per device)
+static int sm_count() {
+    static std::atomic<int> sms_of[kMaxDevices];
+    const int dev = current_device();
+    int n = sms_of[dev].load(std::memory_order_acquire);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms_of[dev].store(n, std::memory_order_release);
+    }
+    return n;
 }
 
 static bool multi_supported(int Lx, int L) {
@@ -484,10 +501,15 @@ static int leapfrog_steps(const double* th_in, const double* pi_in, double* thA,
 constexpr int kSumThreads = 256;
 constexpr int kSumRowsPerBlock = 16;
 
+// DRIFT: the sums are those of theta' = regularize(theta + a*pi) (last half drift of hmc_u1.py:78-79 fused into the
+// H_new reduction of the slab path); theta' of the block's own sites is written to `tho` (same plane stride), and
+// the neighbours' theta' entering a plaquette are recomputed in registers.  Needs dn_in_place (theta AND pi of the
+// row after the last own row are read in place).
+template <bool DRIFT>
 __global__ void __launch_bounds__(kSumThreads)
 k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
                const double* __restrict__ pi, double* __restrict__ partial, int Lx, int L, int nblk, int rpb,
-               size_t plane, int dn_in_place) {
+               size_t plane, int dn_in_place, double a, double* __restrict__ tho) {
     // plane = distance between the mu=0 and mu=1 planes (Lx*L for a contiguous field; larger inside a slab's
     // halo-extended buffer, where the row after the last own row IS the lower neighbour's first row).
     __shared__ double red[3 * 32];
@@ -503,8 +525,20 @@ k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
         double t1dn;
         if (x + 1 < Lx || dn_in_place) t1dn = t1[(size_t)(x + 1) * L + y];
         else t1dn = th_dn ? th_dn[L + y] : t1[y];
+        double a00 = t0[(size_t)x * L + y], b00 = t1[(size_t)x * L + y], a01 = t0[(size_t)x * L + yp];
+        if (DRIFT) {
+            const double* q0 = pi + (size_t)blockIdx.y * 2 * V;
+            const double* q1 = q0 + V;
+            a00 = wrap_pi(fma(a, q0[(size_t)x * L + y], a00));
+            b00 = wrap_pi(fma(a, q1[(size_t)x * L + y], b00));
+            a01 = wrap_pi(fma(a, q0[(size_t)x * L + yp], a01));
+            t1dn = wrap_pi(fma(a, q1[(size_t)(x + 1) * L + y], t1dn));
+            double* o0 = tho + (size_t)blockIdx.y * 2 * V;
+            o0[(size_t)x * L + y] = a00;
+            o0[V + (size_t)x * L + y] = b00;
+        }
         // cos(wrap P) = cos P; wrap_fast agrees with utils.py:182-187 to its rounding (u1_fastmath.cuh)
-        const double P = t0[(size_t)x * L + y] - t1[(size_t)x * L + y] - t0[(size_t)x * L + yp] + t1dn;
+        const double P = a00 - b00 - a01 + t1dn;
         v[0] += fast_cos(P);
         v[1] += wrap_fast(P);
         if (pi) {
@@ -551,8 +585,9 @@ static int launch_sums(const double* th, const double* th_dn, const double* pi, 
     const size_t pl = plane ? plane : (size_t)Lx * L;
     for (int b0 = 0; b0 < B; b0 += kMaxGridY) {            // chains ride in gridDim.y (<= 65535 per launch)
         const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
-        k_partial_sums<<<dim3(nblk, nb), kSumThreads, 0, st>>>(th + (size_t)b0 * 2 * pl, th_dn, pi ? pi + (size_t)b0 * 2 * pl : nullptr,
-                                                               partial + (size_t)b0 * nblk * 3, Lx, L, nblk, rpb, pl, dn_in_place);
+        k_partial_sums<false><<<dim3(nblk, nb), kSumThreads, 0, st>>>(th + (size_t)b0 * 2 * pl, th_dn, pi ? pi + (size_t)b0 * 2 * pl : nullptr,
+                                                                      partial + (size_t)b0 * nblk * 3, Lx, L, nblk, rpb, pl, dn_in_place,
+                                                                      0.0, nullptr);
         count_launch();
         U1_CHECK_LAUNCH();
     }
@@ -1225,6 +1260,42 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
     return U1_OK;
 }
 
+int u1_slab_drift_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* theta_out_own,
+                           double a, double* sums, int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_own || !pi_own || !theta_out_own || !sums || Lx <= 0 || L <= 0 || plane_stride < (size_t)(Lx + 1) * L)
+        return U1_ERR_ARG;
+    if (theta_out_own == theta_own) return U1_ERR_ARG;          // neighbours' pre-drift values are still being read
+    const size_t need = (size_t)sum_blocks(1, Lx) * 3 * sizeof(double);
+    U1_TRY(check_ws(ws, ws_bytes, need));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rpb = sum_rows_per_block(1, Lx), nblk = (Lx + rpb - 1) / rpb;
+    k_partial_sums<true><<<dim3(nblk, 1), kSumThreads, 0, st>>>(theta_own, nullptr, pi_own, (double*)ws, Lx, L, nblk, rpb,
+                                                                plane_stride, 1, a, theta_out_own);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    k_finish_sums<<<1, 128, 0, st>>>((const double*)ws, sums, nblk);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_leapfrog_steps_rect3(const double* theta_in, const double* pi_in, double* thetaA, double* piA, double* thetaB,
+                            double* piB, int B, int Lx, int L, double beta, double first_drift, double dt, int n,
+                            int* result_in_B, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !thetaA || !piA || !thetaB || !piB || !result_in_B || B <= 0 || L <= 0 || Lx <= 0 || n < 1)
+        return U1_ERR_ARG;
+    if (thetaA == thetaB || piA == piB || theta_in == thetaA || theta_in == thetaB || pi_in == piA || pi_in == piB) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(thetaA) || !aligned16(piA) || !aligned16(thetaB) || !aligned16(piB))
+        return U1_ERR_ARG;
+    const double *ct = nullptr, *cp = nullptr;
+    U1_TRY(leapfrog_steps(theta_in, pi_in, thetaA, piA, thetaB, piB, B, Lx, L, beta, first_drift, dt, n,
+                          (cudaStream_t)stream, &ct, &cp));
+    *result_in_B = (ct == thetaB) ? 1 : 0;
+    return U1_OK;
+}
+
 int u1_leapfrog_multi_tile_rows(int Lx) { return Lx > 0 ? (Lx + kMsOut - 1) / kMsOut : 0; }
 
 int u1_leapfrog_multi_rows(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
@@ -1420,7 +1491,8 @@ int u1_plain_preload_slab_kernels(void) {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<64>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_finish_sums);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_momenta_rows);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_metropolis);

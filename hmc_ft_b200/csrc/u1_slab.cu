@@ -208,6 +208,17 @@ __global__ void k_slab_select_planes(double* __restrict__ own, const double* __r
         own[i] = ext[mu * plane + j];
     }
 }
+// on accept: state[mu][j] = src[mu][j] (both plane-strided) and, if given, the caller's contiguous copy own[i] too
+__global__ void k_slab_select_state(double* __restrict__ state, const double* __restrict__ src, size_t plane, size_t n,
+                                    double* __restrict__ own, const int32_t* __restrict__ acc) {
+    if (!acc[0]) return;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t mu = i / n, j = i - mu * n;
+        const double v = src[mu * plane + j];
+        state[mu * plane + j] = v;
+        if (own) own[i] = v;
+    }
+}
 __global__ void k_slab_copy_in(const double* __restrict__ own, double* __restrict__ ext, size_t plane, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t mu = i / n, j = i - mu * n;
@@ -276,6 +287,7 @@ int u1_slab_preload(void) {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_drift_wrap_planes);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_select_planes);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_copy_in);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_slab_select_state);
     if (e != cudaSuccess) return (int)e;
     return u1_plain_preload_slab_kernels();
 }
@@ -345,6 +357,17 @@ int u1_slab_select(double* theta_own, const double* ext_theta_own, size_t plane_
     if (!theta_own || !ext_theta_own || !accept || Lx <= 0 || L <= 0 || plane_stride < (size_t)Lx * L) return U1_ERR_ARG;
     const size_t n = (size_t)Lx * L;
     k_slab_select_planes<<<slab_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(theta_own, ext_theta_own, plane_stride, n, accept);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+
+int u1_slab_select_state(double* state_own, const double* src_own, size_t plane_stride, double* theta_own, int Lx, int L,
+                         const int32_t* accept, u1_stream_t stream) {
+    g_launches = 0;
+    if (!state_own || !src_own || !accept || Lx <= 0 || L <= 0 || plane_stride < (size_t)Lx * L) return U1_ERR_ARG;
+    const size_t n = (size_t)Lx * L;
+    k_slab_select_state<<<slab_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(state_own, src_own, plane_stride, n, theta_own, accept);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;

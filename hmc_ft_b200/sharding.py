@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import math
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -238,8 +239,13 @@ class SlabHMC:
         self.halo.world, self.halo.rank = self.world, self.rank
         self.halo.up, self.halo.dn = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         Lxe = self.Lx + 2 * self.k
-        # ext[f][mu][row][y], f = 0 theta, 1 pi ; two buffers for the out-of-place step kernel
+        # ext[f][mu][row][y], f = 0 theta, 1 pi ; two work buffers for the out-of-place step kernels, and the state
+        # buffer: _st[0] = the accepted theta (kept in extended layout between trajectories, so a trajectory starts
+        # without a copy-in and the steps read it in place), _st[1] = the fresh momenta of the current trajectory
         self._ext = [torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev) for _ in range(2)]
+        self._st = torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev)
+        self._state_ref = None                     # weakref to the caller's theta_own the state was taken from
+        self._state_version = -1
         self._sums6 = torch.zeros(6, dtype=torch.float64, device=self._dev)     # [old sums | new sums]
         # private scratch for the sums kernels: a captured graph bakes this pointer in, so it must not be a
         # shared grow-only cache entry
@@ -326,7 +332,12 @@ class SlabHMC:
         trajectory index lives in a device counter that the graph increments (u1_momenta_rows_dev /
         u1_slab_metropolis_peer) and the exchange epochs in the peer region, so the replay draws fresh momenta
         and a fresh accept uniform.  `U1_SLAB_GRAPH=0`, an injected `u`, or a failed capture keep the eager
-        path.  Every rank must call trajectory() the same number of times."""
+        path.  Every rank must call trajectory() the same number of times.
+
+        The accepted state also lives in an extended-layout buffer of this object; theta_own is copied in only when
+        it is a different tensor than last time or torch has seen an in-place write to it since (tensor version
+        counter).  After writing to theta_own through a raw pointer call invalidate_state()."""
+        self._sync_state(theta_own)
         if self._graph_mode and u is None and theta_own.is_cuda:
             key = (theta_own.data_ptr(), tuple(theta_own.shape), torch.cuda.current_stream(self._dev).cuda_stream)
             g = self._graph
@@ -338,6 +349,21 @@ class SlabHMC:
                     return self._replay(g)
         self._eager_calls += 1
         return self._trajectory_body(theta_own, u, self.traj_counter, None)
+
+    def invalidate_state(self) -> None:
+        """Forget the internal copy of the state: the next trajectory() copies theta_own in again."""
+        self._state_ref = None
+
+    def _sync_state(self, theta_own: torch.Tensor) -> None:
+        ref = self._state_ref() if self._state_ref is not None else None
+        if ref is theta_own and theta_own._version == self._state_version:
+            return
+        k, Lx, L = self.k, self.Lx, self.L
+        with torch.cuda.device(self._dev):
+            self._call(self._lib.u1_slab_copy_in(theta_own.data_ptr(), self._st[0, 0, k].data_ptr(), (Lx + 2 * k) * L, Lx, L,
+                                                 stream_ptr(self._dev)), "u1_slab_copy_in")
+        self._state_ref = weakref.ref(theta_own)
+        self._state_version = theta_own._version
 
     def prepare_graph(self, theta_own: torch.Tensor) -> bool:
         """Capture the trajectory graph now (no replay).  trajectory() does this by itself on its third call; a
@@ -396,34 +422,35 @@ class SlabHMC:
 
     def _trajectory_body(self, theta_own: torch.Tensor, u: Optional[float], traj: int,
                          ctr: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """All device work of one trajectory, operating in place on the halo-extended buffers: copy-in,
-        momenta, theta halo exchange, H_old sums, blocks of <= k fused steps with a (theta,pi) exchange in
-        between, final drift in place, one-row theta exchange, H_new sums, cross-rank sum + Metropolis, select."""
+        """All device work of one trajectory on the halo-extended buffers (the state is already in self._st[0]):
+        momenta, theta halo exchange, H_old sums, blocks of <= k fused steps with a (theta,pi) exchange in between
+        (the first block reads the state in place), one-row (theta,pi) exchange, final drift fused into the H_new
+        sums, cross-rank sum + Metropolis, select into the state and the caller's theta_own."""
         L, Lx, k, dt = self.L, self.Lx, self.k, self.dt
         lib, dev = self._lib, self._dev
         ctr_p = None if ctr is None else ctr.data_ptr()
         cur, nxt = self._ext
+        st = self._st
         plane = (Lx + 2 * k) * L                             # doubles between the mu planes of an ext buffer
         s6 = self._sums6
         peer = self.transport == "peer"
         with torch.cuda.device(dev):
             sp = stream_ptr(dev)
             ws, nb = self._ws.data_ptr(), self._ws.numel()
-            self._call(lib.u1_slab_copy_in(theta_own.data_ptr(), cur[0, 0, k].data_ptr(), plane, Lx, L, sp), "u1_slab_copy_in")
             # theta halo exchange on the side stream, concurrent with the momenta kernel (it only writes pi)
             main = torch.cuda.current_stream(dev)
             side = self._side if self._overlap else None
             if side is not None:
                 side.wait_stream(main)
-                self._exchange(cur, False, k, k, side.cuda_stream)
+                self._exchange(st, False, k, k, side.cuda_stream)
             # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
-            self._call(lib.u1_momenta_rows_dev(cur[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
+            self._call(lib.u1_momenta_rows_dev(st[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
                                                Lx + 2 * k, L, L, sp), "u1_momenta_rows")
             if side is not None:
                 main.wait_stream(side)
             else:
-                self._exchange(cur, False, k, k, sp)         # theta halos
-            self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
+                self._exchange(st, False, k, k, sp)          # theta halos
+            self._call(lib.u1_slab_sums_ext(st[0, 0, k].data_ptr(), st[1, 0, k].data_ptr(), plane,
                                             s6[0:3].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
             done = 0
             while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
@@ -447,24 +474,32 @@ class SlabHMC:
                     cur, nxt = nxt, cur
                 elif done > 0:
                     self._exchange(cur, True, k, k, sp)      # theta and pi, k rows each side
-                if nblk > first:
+                if done == 0:
+                    in_b = C.c_int(0)                        # reads the state in place, first output into cur
+                    self._call(lib.u1_leapfrog_steps_rect3(st[0].data_ptr(), st[1].data_ptr(), cur[0].data_ptr(),
+                                                           cur[1].data_ptr(), nxt[0].data_ptr(), nxt[1].data_ptr(), 1,
+                                                           Lx + 2 * k, L, self.beta, 0.5 * dt, dt, nblk, C.byref(in_b), sp),
+                               "u1_leapfrog_steps_rect3")
+                    if in_b.value:
+                        cur, nxt = nxt, cur
+                elif nblk > first:
                     in_b = C.c_int(0)
                     self._call(lib.u1_leapfrog_steps_rect(cur[0].data_ptr(), cur[1].data_ptr(), nxt[0].data_ptr(),
                                                           nxt[1].data_ptr(), 1, Lx + 2 * k, L, self.beta,
-                                                          0.5 * dt if done == 0 else dt, dt, nblk - first, C.byref(in_b), sp),
+                                                          dt, dt, nblk - first, C.byref(in_b), sp),
                                "u1_leapfrog_steps_rect")
                     if in_b.value:
                         cur, nxt = nxt, cur
                 done += nblk
-            # final half drift + wrap on own rows, in place (hmc_u1.py:78-79), then H_new
-            self._call(lib.u1_slab_drift_wrap(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane, Lx, L, 0.5 * dt, sp),
-                       "u1_slab_drift_wrap")
+            # final half drift + wrap (hmc_u1.py:78-79) fused into the H_new sums: the proposal theta' of the own rows
+            # goes to nxt; the plaquettes of the last own row need (theta, pi) of the lower neighbour's first row
             if peer:
-                self._exchange(cur, False, 1, 0, sp)         # H_new only reads the lower neighbour's first row
+                self._exchange(cur, True, 1, 0, sp)
             else:
-                self._exchange(cur, False, k, k, sp)
-            self._call(lib.u1_slab_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
-                                            s6[3:6].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
+                self._exchange(cur, True, k, k, sp)
+            self._call(lib.u1_slab_drift_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
+                                                  nxt[0, 0, k].data_ptr(), 0.5 * dt, s6[3:6].data_ptr(), Lx, L, ws, nb, sp),
+                       "u1_slab_drift_sums_ext")
             out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
             out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
             u_d = None if u is None else torch.tensor([float(u)], dtype=torch.float64, device=dev)
@@ -484,10 +519,8 @@ class SlabHMC:
                                                       out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
                                                       out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
                            "u1_metropolis_sums")
-            self._call(lib.u1_slab_select(theta_own.data_ptr(), cur[0, 0, k].data_ptr(), plane, Lx, L,
-                                          out["accept"].data_ptr(), sp), "u1_slab_select")
+            self._call(lib.u1_slab_select_state(st[0, 0, k].data_ptr(), nxt[0, 0, k].data_ptr(), plane, theta_own.data_ptr(),
+                                                Lx, L, out["accept"].data_ptr(), sp), "u1_slab_select_state")
         if ctr is None:
-            # (under capture the buffer roles must stay as they were: every replay starts from them)
-            self._ext = [cur, nxt]
             self.traj_counter += 1
         return out

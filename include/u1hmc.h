@@ -139,6 +139,17 @@ int u1_leapfrog_step_rect(const double* theta_in, const double* pi_in, double* t
 int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* piB,
                            int B, int Lx, int L, double beta, double first_drift, double dt, int n,
                            int* result_in_B, u1_stream_t stream);
+/* u1_leapfrog_steps_rect with a read-only input pair: the steps start from (theta_in, pi_in), which are left
+ * untouched, and ping-pong between (thetaA, piA) (first output) and (thetaB, piB).  The slab path keeps the accepted
+ * state in place this way (no copy into a work buffer at the start of a trajectory). */
+int u1_leapfrog_steps_rect3(const double* theta_in, const double* pi_in, double* thetaA, double* piA, double* thetaB,
+                            double* piB, int B, int Lx, int L, double beta, double first_drift, double dt, int n,
+                            int* result_in_B, u1_stream_t stream);
+/* u1_slab_sums_ext of theta' = regularize(theta + a*pi) (hmc_u1.py:78-79 fused into the H_new reduction): theta' of
+ * the own rows is written to theta_out_own (same plane stride, a different buffer), sums[0..2] as u1_slab_sums_ext.
+ * theta AND pi of the row after the last own row are read in place (exchange one (theta, pi) row first). */
+int u1_slab_drift_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* theta_out_own,
+                           double a, double* sums, int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
 /* One launch of the temporally blocked kernel restricted to tile rows [tile_row0, tile_row0 + tile_rows) of the
  * u1_leapfrog_multi_tile_rows(Lx) rows of 56-row tiles: ksteps <= 4 leapfrog steps (first drift first_drift, then
  * dt) from (theta_in, pi_in) to (theta_out, pi_out); a tile row reads rows [56 i - 4, 56 i + 60) (periodic) and
@@ -236,6 +247,10 @@ int u1_slab_metropolis_peer(const double* sums_old, const double* sums_new, cons
 int u1_slab_drift_wrap(double* ext_theta_own, const double* ext_pi_own, size_t plane_stride, int Lx, int L, double a,
                        u1_stream_t stream);
 int u1_slab_copy_in(const double* theta_own, double* ext_theta_own, size_t plane_stride, int Lx, int L, u1_stream_t stream);
+/* select into a state kept in extended layout: state_own = src_own where *accept != 0 (both plane-strided), and the
+ * caller's contiguous theta_own [2][Lx][L] as well when it is not NULL. */
+int u1_slab_select_state(double* state_own, const double* src_own, size_t plane_stride, double* theta_own, int Lx, int L,
+                         const int32_t* accept, u1_stream_t stream);
 int u1_slab_select(double* theta_own, const double* ext_theta_own, size_t plane_stride, int Lx, int L,
                    const int32_t* accept, u1_stream_t stream);
 

@@ -9,8 +9,14 @@ The run is 6 trajectories, so with graphs on (default) it covers 2 eager passes,
 import os
 import sys
 
-import torch
-import torch.distributed as dist
+# Virtual ranks spin on each other's flags from separate streams of ONE GPU: every stream (main + side stream per
+# rank) must own a hardware work queue, or a spinning kernel at the head of a shared queue holds back the very
+# kernel it waits for.  The default is 8 queues; 8 virtual ranks use 16 streams.  (Real ranks have a GPU each.)
+if len(sys.argv) > 4 and int(sys.argv[4]) > 1:
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
