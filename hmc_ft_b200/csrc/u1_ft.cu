@@ -45,17 +45,24 @@ enum { EPI_GELU = 0, EPI_FINAL = 1, EPI_BWD = 2 };
 //                   phi even): 137 intervals of width 1/16, degree 9 (truncation < 1e-18 for Psi,
 //                   < 3e-17 for phi): 17 DFMA + 10 LDS per value, |z| and the clamp done on the integer
 //                   pipe (no fmin/fmax), absolute accuracy like 0.5*(1+erf) itself.
+//   U1_GELU_V == 3: the same odd-part table with 273 intervals of width 1/32 and degree 7 (truncation < 1e-19 for
+//                   Psi, < 1e-17 for phi; 19.7 KB of shared memory instead of 12 KB): 13 DFMA + 8 LDS per value.
+//                   Against 40-digit references on 40 000 points in [-9, 9] all three variants have the same maximum
+//                   absolute error, 1.8e-15 (GELU) / 7.3e-16 (GELU'), i.e. the rounding of z*Phi itself.
 // |z| > 8.5 is clamped: Phi(-8.5) = 9.5e-18, phi(8.5) = 8e-17.
 // ---------------------------------------------------------------------------------------
 #ifndef U1_GELU_V
-#define U1_GELU_V 2
+#define U1_GELU_V 3
 #endif
 #if U1_GELU_V == 1
 constexpr int kGeluIntervals = 137, kGeluDeg = 11, kGeluStride = 13;   // odd stride: conflict-free banks
 constexpr double kGeluZmax = 8.5, kGeluInvH = 8.0;
-#else
+#elif U1_GELU_V == 2
 constexpr int kGeluIntervals = 137, kGeluDeg = 9, kGeluStride = 11;
 constexpr double kGeluZmax = 8.5, kGeluInvH = 16.0;
+#else
+constexpr int kGeluIntervals = 273, kGeluDeg = 7, kGeluStride = 9;
+constexpr double kGeluZmax = 8.5, kGeluInvH = 32.0;
 #endif
 constexpr int kGeluTableDoubles = (kGeluIntervals * kGeluStride + 1) & ~1;   // even: moved in 16-byte chunks
 
@@ -97,7 +104,7 @@ static void build_gelu_table(double* out) {
     }
 }
 #else
-// Interval i is centred at i/16 (i = 0..136); i = rint(16 |z|) is the low word of 16|z| + 1.5*2^52.
+// Interval i is centred at i/InvH (InvH = 16 or 32); i = rint(InvH |z|) is the low word of InvH|z| + 1.5*2^52.
 // |z| is clamped to 8.5 by an unsigned min on the high word (doubles >= 0 order like their bit patterns).
 __device__ __forceinline__ void gelu_and_grad(const double* __restrict__ tab, double z, double& a, double& d) {
     constexpr double kMagic = 6755399441055744.0;
@@ -607,6 +614,94 @@ k_ft_update(const double* __restrict__ th, const double* __restrict__ K, double*
     }
 }
 
+// Final convolution + subset update in one kernel (forward sweep of the sampler): the thread that evaluates the six K
+// channels of an active site is the only consumer of those values in k_ft_update, so it goes on to form Delta and
+// log(1+J) itself and writes theta^(k+1) for its 2x2 block of sites (the active site and its three inactive
+// neighbours), instead of K making a round trip through memory and a second kernel re-reading theta.  Kout / dout
+// (needed by the reverse pass) are written only when dout != nullptr.  Same arithmetic, in the same order, as
+// k_conv_final_sparse followed by k_ft_update (mode 0); only the grouping of the log-det partial sums differs
+// (128 active sites per CTA instead of 256 sites).  Needs (L*L/4) % 128 == 0, i.e. L a multiple of 32.
+__global__ void __launch_bounds__(kConvThreads)
+k_final_update(const __grid_constant__ ConvP<kW, kActCh> p, const double* __restrict__ in,
+               const double* __restrict__ th, double* __restrict__ th_out,
+               double* __restrict__ Kout, double* __restrict__ dout, double* __restrict__ partial,
+               const double* __restrict__ gelu_tab, int k, int L) {
+    extern __shared__ double s_tab[];
+    __shared__ double red[32];
+    asm volatile("griddepcontrol.launch_dependents;");
+    for (int i = threadIdx.x; i < kGeluTableDoubles; i += kConvThreads) s_tab[i] = gelu_tab[i];
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int t = blockIdx.x * kConvThreads + threadIdx.x;
+    const int V = L * L, H = L >> 1, QV = V >> 2;
+    const Subset ss = subset_of(k);
+    const int b = t / QV, q = t - b * QV;
+    const int xa = q / H, ya = q - xa * H;
+    const int x = 2 * xa + ss.a, y = 2 * ya + ss.b;
+    const int xr[3] = {(x == 0 ? L - 1 : x - 1) * L, x * L, (x == L - 1 ? 0 : x + 1) * L};
+    const int yc[3] = {(y == 0 ? L - 1 : y - 1), y, (y == L - 1 ? 0 : y + 1)};
+    const double* ib = in + (size_t)b * kW * V;
+    double acc[kActCh];
+#pragma unroll
+    for (int j = 0; j < kActCh; ++j) acc[j] = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < kW; ++c) {
+        const double* pc = ib + (size_t)c * V;
+        double v[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i * 3 + j] = pc[xr[i] + yc[j]];
+        const double* w = p.w + c * 9 * kActCh;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+            for (int j = 0; j < kActCh; ++j) acc[j] = fma(w[tp * kActCh + j], v[tp], acc[j]);
+    }
+    const double* t0 = th + (size_t)b * 2 * V;
+    Lat g{t0, t0 + V, L};
+    LinkTerms lt;
+    link_terms(g, ss.mu, x, y, lt);
+    const int r = x * L + y;
+    const size_t ob = (size_t)b * kW * V + r;
+    double d[6], jj[6];
+#pragma unroll
+    for (int j = 0; j < kActCh; ++j) {
+        double gg, dd;
+        gelu_and_grad(s_tab, acc[j] + p.b[j], gg, dd);
+        const double kq = atan(gg) / kPi / 2;                               // cnn_model_opt.py:46
+        if (dout) {
+            const size_t idx = ob + (size_t)term_channel(ss.mu, j) * V;
+            Kout[idx] = kq;
+            dout[idx] = dd / ((1.0 + gg * gg) * kTwoPi);
+        }
+        double sn, cs;
+        fast_sincos(lt.A[j], sn, cs);
+        d[j] = kq * (term_sign(ss.mu, j) * sn);
+        jj[j] = kq * (-cs);
+    }
+    // same association as the reference: (plaq0+plaq1) + (((r0+r1)+r2)+r3)
+    const double delta = (d[0] + d[1]) + (((d[2] + d[3]) + d[4]) + d[5]);
+    const double jac = (jj[0] + jj[1]) + (((jj[2] + jj[3]) + jj[4]) + jj[5]);
+    double ld[1] = {log(1.0 + jac)};
+    // theta^(k+1) of the 2x2 block {x, x^1} x {y, y^1} (x^1: the other site of the pair 2xa, 2xa+1)
+    double* o0 = th_out + (size_t)b * 2 * V;
+    const int xo = (x ^ 1) * L, yo = y ^ 1;
+    const int site[4] = {r, x * L + yo, xo + y, xo + yo};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        double a0 = t0[site[m]], a1 = t0[V + site[m]];
+        if (m == 0) { if (ss.mu == 0) a0 += delta; else a1 += delta; }
+        o0[site[m]] = a0;
+        o0[V + site[m]] = a1;
+    }
+    if (partial) {
+        block_sum<1>(ld, red);
+        const int nblk = QV / kConvThreads;
+        if (threadIdx.x == 0) partial[(size_t)b * nblk + (blockIdx.x - b * nblk)] = ld[0];
+    }
+}
+
 // One fixed-point iteration of the inverse transformation (field_trans_opt.py:245-282):
 // next = curr - ft_phase(iter); per-block partial sums of |next-iter|^2 and |iter|^2.
 __global__ void __launch_bounds__(kUpdThreads)
@@ -965,26 +1060,30 @@ static long long chunk_sites() {
     }
     return t;
 }
-// Chunks are independent, so the trajectory entry point CAN run them on two internal streams ("lanes",
-// U1FT_LANES=2) so that one lane's kernel fills the SMs another lane's kernel leaves idle while it
-// drains.  Off by default: with ~190 launches of 10 KB parameters per force the host launch rate
-// (~6 us per launch) becomes the limit once the per-lane kernels get short.
-static int lanes_for(int B) {
-    static int max_lanes = -1;
-    if (max_lanes < 0) {
+// Chunks are independent, so the trajectory entry point can run them on two internal streams ("lanes"); U1FT_LANES=1|2
+// forces the count, otherwise it is chosen from the batch size (see below).
+static int lanes_for(int B, int L) {
+    static int forced = -2;
+    if (forced == -2) {
         const char* e = getenv("U1FT_LANES");
-        max_lanes = e ? atoi(e) : 1;     // measured: 2 lanes are host-launch-bound below ~256 chains (18.7 -> 16.4 TFLOP/s at 128)
-        if (max_lanes < 1) max_lanes = 1;
-        if (max_lanes > kLanes) max_lanes = kLanes;
+        forced = e ? atoi(e) : -1;
+        if (forced > kLanes) forced = kLanes;
     }
-    return B >= 2 ? max_lanes : 1;
+    if (B < 2) return 1;
+    if (forced >= 1) return forced;
+    // Automatic: two lanes when a layer of the whole batch is only a few waves of CTAs, so that one lane's kernels fill
+    // the SMs the other lane's kernel leaves idle while it drains (L=64 rnet3, trajectories/s on one B200, 1 -> 2 lanes:
+    // 128 chains 351 -> 362, 256 chains 358 -> 374, 512 and 1024 chains unchanged; L=32 LOSES 13-20 %: its kernels are
+    // too short).  The launches come from replayed CUDA graphs, so the host launch rate that made two lanes slower in
+    // round 1 (18.7 -> 16.4 TFLOP/s at 128 chains) no longer matters.
+    return (L >= 64 && (long long)B * L * L <= 256ll * 4096) ? 2 : 1;
 }
 static std::atomic<bool> g_chunk_explicit{false};
 static int chunk_chains(int B, int L) {
     const long long target = chunk_sites();
     long long c = target / ((long long)L * L);
     if (c < 1) c = 1;
-    const int nl = lanes_for(B);
+    const int nl = lanes_for(B, L);
     long long nchunks = (B + c - 1) / c;
     if (nchunks < nl) nchunks = nl;
     if (nchunks % nl) nchunks += nl - nchunks % nl;
@@ -1158,7 +1257,8 @@ static int launch_final_bwd_sparse(const ConvP<kW, kW>& pT, int k, const double*
 }
 
 // CNN forward of subset k on chunk of C chains: X -> K (w.Kk[k]).  store!=0 keeps GELU' for backward.
-static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool store, cudaStream_t st) {
+static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool store, cudaStream_t st,
+                       bool skip_final = false) {
     const int ns = C * L * L, nl = h->n_layers;
     auto D = [&](int layer) { return store ? Dbuf(w, nl, C, L, k, layer) : nullptr; };
     const ConvP<kW, kW>* fk = &h->f[(size_t)k * (nl - 1)];
@@ -1168,7 +1268,7 @@ static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool
         U1_TRY((launch_conv<kW, kW, EPI_GELU>(h, fk[2 * i + 1], w.Bf, w.A, nullptr, w.A, D(2 + 2 * i), ns, L, st)));
     }
     (void)fk;
-    U1_TRY(launch_final_sparse(h, k, w.A, w.Kk[k], D(nl - 1), ns, L, st));     // active sites / channels only
+    if (!skip_final) U1_TRY(launch_final_sparse(h, k, w.A, w.Kk[k], D(nl - 1), ns, L, st));     // active sites / channels only
     return U1_OK;
 }
 
@@ -1191,19 +1291,43 @@ static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cud
     return U1_OK;
 }
 
+// U1FT_FUSE (default 1): final convolution + subset update in one kernel where the lattice allows it.
+static bool fuse_final_update(int L) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_FUSE"); v = e ? atoi(e) : 1; }
+    return v != 0 && ((L * L / 4) % kConvThreads == 0);
+}
+
 // Forward sweep over the 8 subsets for a chunk: theta (w.th[0]) -> w.th[8], logdet.
 static int ft_forward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, bool store, bool want_logdet,
                             cudaStream_t st) {
-    const int V = L * L, ns = C * V, nblk = blocks_for(V, kUpdThreads);
+    const int V = L * L, ns = C * V;
+    const bool fused = fuse_final_update(L);
+    const int nblk = fused ? (V / 4) / kConvThreads : blocks_for(V, kUpdThreads);    // log-det partials per chain and subset
     for (int k = 0; k < 8; ++k) {
+        // (computing the features inside the first convolution - six smem tiles formed from theta - was measured
+        // and is 0.3 % SLOWER than this separate 20 us kernel: profiles/r02_ft_fusion_ab.log)
         k_ft_features<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[k], w.X, k, ns, L);
         count_launch();
         U1_CHECK_LAUNCH();
-        U1_TRY(cnn_forward(h, w, k, C, L, store, st));
-        k_ft_update<<<dim3(nblk, C), kUpdThreads, 0, st>>>(w.th[k], w.Kk[k], w.th[k + 1],
-                                                           want_logdet ? w.partial + (size_t)k * C * nblk : nullptr, k, L, nblk, 0);
-        count_launch();
-        U1_CHECK_LAUNCH();
+        U1_TRY(cnn_forward(h, w, k, C, L, store, st, fused));
+        double* part = want_logdet ? w.partial + (size_t)k * C * nblk : nullptr;
+        if (fused) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute attr[1];
+            pdl_config(cfg, attr, (ns >> 2) / kConvThreads, (size_t)kGeluTableDoubles * sizeof(double), st);
+            const double* tab = h->gelu_tab;
+            const double* in = w.A;
+            const double* th = w.th[k];
+            double* dfin = store ? Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1) : nullptr;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_final_update, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k, L);
+            count_launch();
+            if (e != cudaSuccess) return (int)e;
+        } else {
+            k_ft_update<<<dim3(nblk, C), kUpdThreads, 0, st>>>(w.th[k], w.Kk[k], w.th[k + 1], part, k, L, nblk, 0);
+            count_launch();
+            U1_CHECK_LAUNCH();
+        }
     }
     if (want_logdet) {
         k_ft_logdet_accum<<<blocks_for(C, 128), 128, 0, st>>>(w.partial, w.logdet, C, nblk);
@@ -1459,7 +1583,7 @@ int u1ft_destroy(u1ft_handle_t h) {
 
 size_t u1ft_workspace_bytes(u1ft_handle_t h, int B, int L, int with_backward) {
     if (!handle_ok(h) || B <= 0 || L <= 0) return 0;
-    return (size_t)lanes_for(B) * carve_ft(nullptr, h->n_layers, chunk_chains(B, L), L, with_backward != 0).bytes;
+    return (size_t)lanes_for(B, L) * carve_ft(nullptr, h->n_layers, chunk_chains(B, L), L, with_backward != 0).bytes;
 }
 
 int u1ft_forward(u1ft_handle_t h, const double* theta, double* theta_ori, double* logdet,
@@ -1676,7 +1800,7 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
     if (!theta || B <= 0 || L <= 0 || n_traj < 1 || n_steps < 1) return U1_ERR_ARG;
     if (L & 1) return U1_ERR_SHAPE;
     const int Cmax = chunk_chains(B, L);
-    const int nlanes = lanes_for(B);
+    const int nlanes = lanes_for(B, L);
     const size_t lane_bytes = carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes;
     U1_TRY(check_ws_ft(ws, ws_bytes, (size_t)nlanes * lane_bytes));
     cudaStream_t user = (cudaStream_t)stream;
