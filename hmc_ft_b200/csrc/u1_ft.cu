@@ -818,6 +818,98 @@ k_ft_update_bwd(const double* __restrict__ th, const double* __restrict__ K,
     }
 }
 
+// k_ft_update_bwd + k_conv_final_bwd_sparse in one kernel (reverse sweep of the sampler).  A CTA owns TAX = 128/H
+// rows of active sites (H = L/2 active sites per row, all of them: the y direction wraps inside the CTA) and has one
+// extra warp group for the row below: (TAX+1)*H threads each form zbar (6 channels) of ONE active site exactly as
+// k_ft_update_bwd does and park it in shared memory; the TAX*H owner threads also write AP / AR.  After the barrier
+// the owner threads run the transposed final convolution of their 2x2 output block from the four zbar entries in
+// shared memory - same operations in the same order as k_conv_final_bwd_sparse, so the result is bit-identical -
+// and zbar itself never goes to memory.  H in {16, 32, 64}.
+template <int H>
+__global__ void __launch_bounds__(kConvThreads + H)
+k_final_bwd_fused(const __grid_constant__ ConvP<kW, kW> pT, const double* __restrict__ th, const double* __restrict__ K,
+                  const double* __restrict__ dfin, const double* __restrict__ g, const double* __restrict__ mul,
+                  double* __restrict__ out, double* __restrict__ AP, double* __restrict__ AR, int k) {
+    constexpr int L = 2 * H, V = L * L, TAX = kConvThreads / H, NBLK = H / TAX;      // NBLK CTAs per chain
+    __shared__ double zs[kActCh][(TAX + 1) * H];
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const Subset ss = subset_of(k);
+    const int b = blockIdx.x / NBLK, xa0 = (blockIdx.x - b * NBLK) * TAX;
+    const int tid = threadIdx.x, rx = tid / H, ya = tid - rx * H;
+    const bool owner = rx < TAX;
+    const int xa = (xa0 + rx) % H;
+    const int X0 = 2 * xa + ss.a, Y0 = 2 * ya + ss.b;
+    {
+        const int r = X0 * L + Y0;
+        const double* t0 = th + (size_t)b * 2 * V;
+        Lat gl{t0, t0 + V, L};
+        LinkTerms t;
+        link_terms(gl, ss.mu, X0, Y0, t);
+        const double* Kb = K + (size_t)b * kW * V + r;
+        const double* db = dfin + (size_t)b * kW * V + r;
+        double sn[6], cs[6], kq[6], jq[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            fast_sincos(t.A[q], sn[q], cs[q]);
+            kq[q] = Kb[(size_t)term_channel(ss.mu, q) * V];
+            jq[q] = kq[q] * (-cs[q]);
+        }
+        const double jac = (jq[0] + jq[1]) + (((jq[2] + jq[3]) + jq[4]) + jq[5]);
+        const double ga = g[(size_t)b * 2 * V + (size_t)ss.mu * V + r];   // adjoint of Delta
+        const double gb = -1.0 / (1.0 + jac);                             // adjoint of J  (S_FT has -log(1+J))
+        double* APb = AP + (size_t)b * V;
+        double* ARb = AR + (size_t)b * V;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double sg = term_sign(ss.mu, q);
+            const int ch = term_channel(ss.mu, q);
+            const double kbar = ga * sg * sn[q] - gb * cs[q];
+            zs[q][tid] = kbar * db[(size_t)ch * V];
+            if (owner) {
+                const double abar = kq[q] * (ga * sg * cs[q] + gb * sn[q]);
+                if (q < 2) APb[t.loc[q]] = abar; else ARb[t.loc[q]] = abar;
+            }
+        }
+    }
+    __syncthreads();
+    if (!owner) return;
+    const int yb = (ya + 1 == H) ? 0 : ya + 1;
+    const int X1 = wrapi(X0 + 1, L), Y1 = wrapi(Y0 + 1, L);
+    double a00[kW], a01[kW], a10[kW], a11[kW];
+#pragma unroll
+    for (int c = 0; c < kW; ++c) { a00[c] = 0.0; a01[c] = 0.0; a10[c] = 0.0; a11[c] = 0.0; }
+#pragma unroll 1
+    for (int j = 0; j < kActCh; ++j) {
+        const int o = term_channel(ss.mu, j);
+        const double z00 = zs[j][rx * H + ya], z01 = zs[j][rx * H + yb];
+        const double z10 = zs[j][(rx + 1) * H + ya], z11 = zs[j][(rx + 1) * H + yb];
+        const double* w = pT.w + o * 9 * kW;          // w[tap'*12 + c], tap' = position of the source relative to the site
+#pragma unroll
+        for (int c = 0; c < kW; ++c) {
+            a00[c] = fma(w[4 * kW + c], z00, a00[c]);
+            a01[c] = fma(w[3 * kW + c], z00, a01[c]);
+            a01[c] = fma(w[5 * kW + c], z01, a01[c]);
+            a10[c] = fma(w[1 * kW + c], z00, a10[c]);
+            a10[c] = fma(w[7 * kW + c], z10, a10[c]);
+            a11[c] = fma(w[0 * kW + c], z00, a11[c]);
+            a11[c] = fma(w[2 * kW + c], z01, a11[c]);
+            a11[c] = fma(w[6 * kW + c], z10, a11[c]);
+            a11[c] = fma(w[8 * kW + c], z11, a11[c]);
+        }
+    }
+    const size_t ob = (size_t)b * kW * V;
+    const int s00 = X0 * L + Y0, s01 = X0 * L + Y1, s10 = X1 * L + Y0, s11 = X1 * L + Y1;
+#pragma unroll
+    for (int c = 0; c < kW; ++c) {
+        const size_t cb = ob + (size_t)c * V;
+        out[cb + s00] = a00[c] * mul[cb + s00];
+        out[cb + s01] = a01[c] * mul[cb + s01];
+        out[cb + s10] = a10[c] * mul[cb + s10];
+        out[cb + s11] = a11[c] * mul[cb + s11];
+    }
+}
+
 // Total plaquette adjoint PT[b][V] of subset k: update angles (AP, AR) + CNN features (Xbar).
 __global__ void k_ft_feat_bwd(const double* __restrict__ th, const double* __restrict__ Xbar,
                               const double* __restrict__ AP, const double* __restrict__ AR,
@@ -1273,12 +1365,12 @@ static int cnn_forward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, bool
 }
 
 // CNN reverse of subset k: zbar (in w.A) -> Xbar (w.X).
-static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cudaStream_t st) {
+static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cudaStream_t st, bool skip_final = false) {
     const int ns = C * L * L, nl = h->n_layers;
     auto D = [&](int layer) { return Dbuf(w, nl, C, L, k, layer); };
     const ConvP<kW, kW>* bk = &h->bt[(size_t)k * (nl - 1)];
     // hbar = convT_final(zbar_f); times GELU' of the layer below
-    U1_TRY(launch_final_bwd_sparse(bk[nl - 2], k, w.A, D(nl - 2), w.Bf, ns, L, st));
+    if (!skip_final) U1_TRY(launch_final_bwd_sparse(bk[nl - 2], k, w.A, D(nl - 2), w.Bf, ns, L, st));
     // now w.Bf = vbar of the last block (or zbar0 for `simple`)
     double* cur = w.Bf;  double* oth = w.A;
     for (int i = h->n_res - 1; i >= 0; --i) {
@@ -1289,6 +1381,33 @@ static int cnn_backward(u1ft_handle_t h, const FtWs& w, int k, int C, int L, cud
     }
     U1_TRY((launch_conv<kW, kXC, EPI_BWD>(h, h->b0[k], cur, nullptr, nullptr, w.X, nullptr, ns, L, st)));
     return U1_OK;
+}
+
+// Reverse-sweep counterpart (k_final_bwd_fused): update adjoint + transposed final convolution, L in {32, 64, 128}.
+static bool fuse_final_bwd(int L) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_FUSE_BWD"); v = e ? atoi(e) : 1; }
+    return v != 0 && (L == 32 || L == 64 || L == 128);
+}
+template <int H>
+static int launch_final_bwd_fused_h(const ConvP<kW, kW>& pT, const double* th, const double* K, const double* dfin,
+                                    const double* g, const double* mul, double* out, double* AP, double* AR, int k, int C,
+                                    cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    pdl_config(cfg, attr, C * (H / (kConvThreads / H)), 0, st);
+    cfg.blockDim = dim3(kConvThreads + H);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_final_bwd_fused<H>, pT, th, K, dfin, g, mul, out, AP, AR, k);
+    count_launch();
+    return e == cudaSuccess ? U1_OK : (int)e;
+}
+static int launch_final_bwd_fused(const ConvP<kW, kW>& pT, const double* th, const double* K, const double* dfin,
+                                  const double* g, const double* mul, double* out, double* AP, double* AR, int k, int C, int L,
+                                  cudaStream_t st) {
+    if (L == 32) return launch_final_bwd_fused_h<16>(pT, th, K, dfin, g, mul, out, AP, AR, k, C, st);
+    if (L == 64) return launch_final_bwd_fused_h<32>(pT, th, K, dfin, g, mul, out, AP, AR, k, C, st);
+    if (L == 128) return launch_final_bwd_fused_h<64>(pT, th, K, dfin, g, mul, out, AP, AR, k, C, st);
+    return U1_ERR_UNSUPPORTED;
 }
 
 // U1FT_FUSE (default 1): final convolution + subset update in one kernel where the lattice allows it.
@@ -1357,12 +1476,19 @@ static int ft_backward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, doubl
     k_plain_force<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[8], g, ns, L, beta);
     count_launch();
     U1_CHECK_LAUNCH();
+    const bool fused = fuse_final_bwd(L);
     for (int k = 7; k >= 0; --k) {
-        k_ft_update_bwd<<<blocks_for(ns, kUpdThreads), kUpdThreads, 0, st>>>(
-            w.th[k], w.Kk[k], Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1), g, w.A, w.AP, w.AR, k, ns, L);
-        count_launch();
-        U1_CHECK_LAUNCH();
-        U1_TRY(cnn_backward(h, w, k, C, L, st));
+        const double* dfin = Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1);
+        if (fused) {
+            const ConvP<kW, kW>& pT = h->bt[(size_t)k * (h->n_layers - 1) + h->n_layers - 2];
+            const double* mul = Dbuf(w, h->n_layers, C, L, k, h->n_layers - 2);
+            U1_TRY(launch_final_bwd_fused(pT, w.th[k], w.Kk[k], dfin, g, mul, w.Bf, w.AP, w.AR, k, C, L, st));
+        } else {
+            k_ft_update_bwd<<<blocks_for(ns, kUpdThreads), kUpdThreads, 0, st>>>(w.th[k], w.Kk[k], dfin, g, w.A, w.AP, w.AR, k, ns, L);
+            count_launch();
+            U1_CHECK_LAUNCH();
+        }
+        U1_TRY(cnn_backward(h, w, k, C, L, st, fused));
         k_ft_feat_bwd<<<blocks_for(ns, 256), 256, 0, st>>>(w.th[k], w.X, w.AP, w.AR, w.PT, k, ns, L);
         count_launch();
         U1_CHECK_LAUNCH();
