@@ -60,7 +60,9 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "u1_slab_drift_wrap": (_i, [_vp, _vp, _sz, _i, _i, _d, _vp]),
     "u1_slab_copy_in": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
-    "u1_slab_select_state": (_i, [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp]),
+    "u1_slab_select_state": (_i, [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "u1_slab_reduce_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "u1_momenta_rows_pi2_dev": (_i, [_vp, _u64, _u64, _u64, _vp, C.c_longlong, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "u1_slab_select": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
     "u1_diff_power_sums_workspace_bytes": (C.c_size_t, []),
     "u1_diff_power_sums": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp]),

@@ -77,11 +77,50 @@ __global__ void k_momenta(double* __restrict__ pi, uint64_t seed, uint64_t chain
     }
 }
 
-__global__ void k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t chain, uint64_t traj,
-                               const uint64_t* __restrict__ traj_dev, long long x_first, int Lx, int L, int Lxg) {
+// Single-pass deterministic reduction for kernels of ONE lattice (the slab path): every block stores its NV partial
+// values and draws a ticket; the block that draws the last ticket adds all partials (fixed order: thread-strided, then
+// block_sum) into out[0..NV) and resets the ticket, so the kernel needs no separate finishing launch and can be
+// replayed from a CUDA graph.  `ticket` must be zero before the first launch.  v[] holds the block totals (valid in
+// thread 0, as block_sum leaves them); red: NV*32 doubles of shared memory.
+template <int NV>
+__device__ __forceinline__ void finish_by_last_block(double (&v)[NV], double* __restrict__ partial, unsigned int* ticket,
+                                                     double* __restrict__ out, double* red, int nblk, int my_block) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partial[(size_t)my_block * NV + k] = v[k];
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == (unsigned)(nblk - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a[k] = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) a[k] += *reinterpret_cast<const volatile double*>(partial + (size_t)i * NV + k);
+    block_sum<NV>(a, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = a[k];
+        *ticket = 0u;
+    }
+}
+
+// SUM: also sum pi^2 over the rows [own0, own0 + own_rows) of the buffer (the slab's own rows; the halo rows get
+// momenta too but belong to the neighbours' Hamiltonian) into pi2_out[0] - H_old's kinetic term without a pass over pi.
+template <bool SUM>
+__global__ void __launch_bounds__(256)
+k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t chain, uint64_t traj,
+               const uint64_t* __restrict__ traj_dev, long long x_first, int Lx, int L, int Lxg,
+               int own0, int own_rows, double* __restrict__ partial, unsigned int* ticket, double* __restrict__ pi2_out) {
+    __shared__ double red[32];
     if (traj_dev) traj += *traj_dev;                  // device-resident trajectory counter (CUDA-graph replay)
     const long long n = (long long)Lx * L;
     const PhiloxKey key = chain_key(seed, chain);
+    double acc[1] = {0.0};
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n;
          s += (long long)gridDim.x * blockDim.x) {
         const int xl = (int)(s / L), y = (int)(s - (long long)xl * L);
@@ -91,6 +130,11 @@ __global__ void k_momenta_rows(double* __restrict__ pi, uint64_t seed, uint64_t 
         philox_site_normals(key, traj, (uint32_t)(xg * L + y), kLogTab, n0, n1);
         pi[s] = n0;
         pi[n + s] = n1;
+        if (SUM && xl >= own0 && xl < own0 + own_rows) acc[0] += n0 * n0 + n1 * n1;
+    }
+    if (SUM) {
+        block_sum<1>(acc, red);
+        finish_by_last_block<1>(acc, partial, ticket, pi2_out, red, (int)gridDim.x, (int)blockIdx.x);
     }
 }
 
@@ -500,16 +544,12 @@ static int leapfrog_steps(const double* th_in, const double* pi_in, double* thA,
 // ---------------------------------------------------------------------------------------
 constexpr int kSumThreads = 256;
 constexpr int kSumRowsPerBlock = 16;
+constexpr size_t kTicketBytes = 256;      // head of a reduction workspace: the ticket word of finish_by_last_block (zero it once)
 
-// DRIFT: the sums are those of theta' = regularize(theta + a*pi) (last half drift of hmc_u1.py:78-79 fused into the
-// H_new reduction of the slab path); theta' of the block's own sites is written to `tho` (same plane stride), and
-// the neighbours' theta' entering a plaquette are recomputed in registers.  Needs dn_in_place (theta AND pi of the
-// row after the last own row are read in place).
-template <bool DRIFT>
 __global__ void __launch_bounds__(kSumThreads)
 k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
                const double* __restrict__ pi, double* __restrict__ partial, int Lx, int L, int nblk, int rpb,
-               size_t plane, int dn_in_place, double a, double* __restrict__ tho) {
+               size_t plane, int dn_in_place) {
     // plane = distance between the mu=0 and mu=1 planes (Lx*L for a contiguous field; larger inside a slab's
     // halo-extended buffer, where the row after the last own row IS the lower neighbour's first row).
     __shared__ double red[3 * 32];
@@ -525,20 +565,8 @@ k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
         double t1dn;
         if (x + 1 < Lx || dn_in_place) t1dn = t1[(size_t)(x + 1) * L + y];
         else t1dn = th_dn ? th_dn[L + y] : t1[y];
-        double a00 = t0[(size_t)x * L + y], b00 = t1[(size_t)x * L + y], a01 = t0[(size_t)x * L + yp];
-        if (DRIFT) {
-            const double* q0 = pi + (size_t)blockIdx.y * 2 * V;
-            const double* q1 = q0 + V;
-            a00 = wrap_pi(fma(a, q0[(size_t)x * L + y], a00));
-            b00 = wrap_pi(fma(a, q1[(size_t)x * L + y], b00));
-            a01 = wrap_pi(fma(a, q0[(size_t)x * L + yp], a01));
-            t1dn = wrap_pi(fma(a, q1[(size_t)(x + 1) * L + y], t1dn));
-            double* o0 = tho + (size_t)blockIdx.y * 2 * V;
-            o0[(size_t)x * L + y] = a00;
-            o0[V + (size_t)x * L + y] = b00;
-        }
         // cos(wrap P) = cos P; wrap_fast agrees with utils.py:182-187 to its rounding (u1_fastmath.cuh)
-        const double P = a00 - b00 - a01 + t1dn;
+        const double P = t0[(size_t)x * L + y] - t1[(size_t)x * L + y] - t0[(size_t)x * L + yp] + t1dn;
         v[0] += fast_cos(P);
         v[1] += wrap_fast(P);
         if (pi) {
@@ -552,6 +580,72 @@ k_partial_sums(const double* __restrict__ th, const double* __restrict__ th_dn,
         double* o = partial + ((size_t)blockIdx.y * nblk + blockIdx.x) * 3;
         o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
     }
+}
+
+// Slab path: the last half drift theta' = regularize(theta + a*pi) (hmc_u1.py:78-79) fused into the H_new sums of ONE
+// lattice slab in extended layout.  A CTA owns kDsRows rows x 256 columns, one thread per column: all loads of its
+// rows are issued up front, every theta' is evaluated once by its owner (the reference's division-based regularize is
+// the expensive part: 2 per site + 1 per column for the row below), theta'_0 of the right neighbour comes through
+// shared memory (the last thread of the CTA evaluates its neighbour column itself) and theta'_1 of the row below is
+// the next row's own value.  theta' of the own sites goes to `tho`; theta AND pi of the row after the last own row
+// are read in place.  The sums land in sums[0..2] through finish_by_last_block (no finishing launch).
+constexpr int kDsRows = 4;
+__global__ void __launch_bounds__(kSumThreads)
+k_drift_sums(const double* __restrict__ th, const double* __restrict__ pi, double* __restrict__ tho, size_t plane,
+             int Lx, int L, double a, double* __restrict__ partial, unsigned int* ticket, double* __restrict__ sums) {
+    __shared__ double red[3 * 32];
+    __shared__ double s_a[kDsRows][kSumThreads + 1];
+    const int tid = threadIdx.x;
+    const int y = blockIdx.x * kSumThreads + tid;
+    const int xa = blockIdx.y * kDsRows;
+    const bool live = y < L;
+    const int yc = live ? y : 0;                               // dead threads shadow column 0
+    const bool edge = live && (tid == kSumThreads - 1 || y + 1 == L);   // right neighbour belongs to another CTA / wraps
+    const int yp = (yc + 1 == L) ? 0 : yc + 1;
+    const double* t0 = th;  const double* t1 = th + plane;
+    const double* q0 = pi;  const double* q1 = pi + plane;
+    double T0[kDsRows], P0[kDsRows], T1[kDsRows + 1], P1[kDsRows + 1], E0[kDsRows], EP[kDsRows];
+#pragma unroll
+    for (int r = 0; r <= kDsRows; ++r) {
+        const int x = min(xa + r, Lx);                         // row Lx = the lower neighbour's first row (in place)
+        const size_t o = (size_t)x * L + yc;
+        T1[r] = t1[o]; P1[r] = q1[o];
+        if (r < kDsRows) {
+            T0[r] = t0[o]; P0[r] = q0[o];
+            E0[r] = 0.0; EP[r] = 0.0;
+            if (edge) { E0[r] = t0[(size_t)x * L + yp]; EP[r] = q0[(size_t)x * L + yp]; }
+        }
+    }
+    double A[kDsRows], Bv[kDsRows + 1];
+#pragma unroll
+    for (int r = 0; r <= kDsRows; ++r) {
+        Bv[r] = wrap_pi(fma(a, P1[r], T1[r]));
+        if (r < kDsRows) {
+            A[r] = wrap_pi(fma(a, P0[r], T0[r]));
+            s_a[r][tid] = A[r];
+        }
+    }
+    if (edge) {
+#pragma unroll
+        for (int r = 0; r < kDsRows; ++r) s_a[r][tid + 1] = wrap_pi(fma(a, EP[r], E0[r]));
+    }
+    __syncthreads();
+    double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < kDsRows; ++r) {
+        const int x = xa + r;
+        if (live && x < Lx) {
+            const size_t o = (size_t)x * L + y;
+            tho[o] = A[r];
+            tho[plane + o] = Bv[r];
+            const double P = A[r] - Bv[r] - s_a[r][tid + 1] + Bv[r + 1];
+            v[0] += fast_cos(P);
+            v[1] += wrap_fast(P);
+            v[2] += P0[r] * P0[r] + P1[r] * P1[r];
+        }
+    }
+    block_sum<3>(v, red);
+    finish_by_last_block<3>(v, partial, ticket, sums, red, (int)(gridDim.x * gridDim.y), (int)(blockIdx.y * gridDim.x + blockIdx.x));
 }
 
 // one CTA per chain: fixed-order (deterministic) reduction of the nblk partial triples
@@ -585,9 +679,8 @@ static int launch_sums(const double* th, const double* th_dn, const double* pi, 
     const size_t pl = plane ? plane : (size_t)Lx * L;
     for (int b0 = 0; b0 < B; b0 += kMaxGridY) {            // chains ride in gridDim.y (<= 65535 per launch)
         const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
-        k_partial_sums<false><<<dim3(nblk, nb), kSumThreads, 0, st>>>(th + (size_t)b0 * 2 * pl, th_dn, pi ? pi + (size_t)b0 * 2 * pl : nullptr,
-                                                                      partial + (size_t)b0 * nblk * 3, Lx, L, nblk, rpb, pl, dn_in_place,
-                                                                      0.0, nullptr);
+        k_partial_sums<<<dim3(nblk, nb), kSumThreads, 0, st>>>(th + (size_t)b0 * 2 * pl, th_dn, pi ? pi + (size_t)b0 * 2 * pl : nullptr,
+                                                               partial + (size_t)b0 * nblk * 3, Lx, L, nblk, rpb, pl, dn_in_place);
         count_launch();
         U1_CHECK_LAUNCH();
     }
@@ -1260,21 +1353,23 @@ int u1_leapfrog_steps_rect(double* thetaA, double* piA, double* thetaB, double* 
     return U1_OK;
 }
 
+size_t u1_slab_reduce_workspace_bytes(int rows, int L) {
+    if (rows <= 0 || L <= 0) return 0;
+    const size_t ds = (size_t)((L + kSumThreads - 1) / kSumThreads) * ((rows + kDsRows - 1) / kDsRows) * 3 * sizeof(double);
+    const size_t mo = (size_t)ew_grid((size_t)rows * L) * sizeof(double);
+    return kTicketBytes + (ds > mo ? ds : mo);
+}
+
 int u1_slab_drift_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* theta_out_own,
                            double a, double* sums, int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream) {
     g_launches = 0;
     if (!theta_own || !pi_own || !theta_out_own || !sums || Lx <= 0 || L <= 0 || plane_stride < (size_t)(Lx + 1) * L)
         return U1_ERR_ARG;
     if (theta_out_own == theta_own) return U1_ERR_ARG;          // neighbours' pre-drift values are still being read
-    const size_t need = (size_t)sum_blocks(1, Lx) * 3 * sizeof(double);
-    U1_TRY(check_ws(ws, ws_bytes, need));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int rpb = sum_rows_per_block(1, Lx), nblk = (Lx + rpb - 1) / rpb;
-    k_partial_sums<true><<<dim3(nblk, 1), kSumThreads, 0, st>>>(theta_own, nullptr, pi_own, (double*)ws, Lx, L, nblk, rpb,
-                                                                plane_stride, 1, a, theta_out_own);
-    count_launch();
-    U1_CHECK_LAUNCH();
-    k_finish_sums<<<1, 128, 0, st>>>((const double*)ws, sums, nblk);
+    const dim3 grid((L + kSumThreads - 1) / kSumThreads, (Lx + kDsRows - 1) / kDsRows);
+    U1_TRY(check_ws(ws, ws_bytes, kTicketBytes + (size_t)grid.x * grid.y * 3 * sizeof(double)));
+    k_drift_sums<<<grid, kSumThreads, 0, (cudaStream_t)stream>>>(theta_own, pi_own, theta_out_own, plane_stride, Lx, L, a,
+                                                                 (double*)((char*)ws + kTicketBytes), (unsigned int*)ws, sums);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
@@ -1314,7 +1409,23 @@ int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj
                         long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream) {
     g_launches = 0;
     if (!pi || Lx <= 0 || L <= 0 || Lx_global <= 0) return U1_ERR_ARG;
-    k_momenta_rows<<<ew_grid((size_t)Lx * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, traj_dev, x_first, Lx, L, Lx_global);
+    k_momenta_rows<false><<<ew_grid((size_t)Lx * L), 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, traj_dev, x_first, Lx, L,
+                                                                                     Lx_global, 0, 0, nullptr, nullptr, nullptr);
+    count_launch();
+    U1_CHECK_LAUNCH();
+    return U1_OK;
+}
+int u1_momenta_rows_pi2_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
+                            long long x_first, int Lx, int L, int Lx_global, int own_first, int own_rows, double* pi2_out,
+                            void* ws, size_t ws_bytes, u1_stream_t stream) {
+    g_launches = 0;
+    if (!pi || !pi2_out || Lx <= 0 || L <= 0 || Lx_global <= 0 || own_first < 0 || own_rows < 0 || own_first + own_rows > Lx)
+        return U1_ERR_ARG;
+    const int grid = ew_grid((size_t)Lx * L);
+    U1_TRY(check_ws(ws, ws_bytes, kTicketBytes + (size_t)grid * sizeof(double)));
+    k_momenta_rows<true><<<grid, 256, 0, (cudaStream_t)stream>>>(pi, seed, chain, traj, traj_dev, x_first, Lx, L, Lx_global, own_first,
+                                                                 own_rows, (double*)((char*)ws + kTicketBytes), (unsigned int*)ws,
+                                                                 pi2_out);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;
@@ -1491,10 +1602,11 @@ int u1_plain_preload_slab_kernels(void) {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<64>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums<false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_finish_sums);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_momenta_rows);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_momenta_rows<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_momenta_rows<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_drift_sums);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_metropolis);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_select);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_final_drift);

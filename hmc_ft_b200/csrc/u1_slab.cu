@@ -209,9 +209,12 @@ __global__ void k_slab_select_planes(double* __restrict__ own, const double* __r
     }
 }
 // on accept: state[mu][j] = src[mu][j] (both plane-strided) and, if given, the caller's contiguous copy own[i] too
+// sums_state[0..1] (sum cos P, sum wrap P of the state: the action part of the next H_old) follow the state
 __global__ void k_slab_select_state(double* __restrict__ state, const double* __restrict__ src, size_t plane, size_t n,
-                                    double* __restrict__ own, const int32_t* __restrict__ acc) {
+                                    double* __restrict__ own, const int32_t* __restrict__ acc,
+                                    double* __restrict__ sums_state, const double* __restrict__ sums_new) {
     if (!acc[0]) return;
+    if (sums_state && blockIdx.x == 0 && threadIdx.x == 0) { sums_state[0] = sums_new[0]; sums_state[1] = sums_new[1]; }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t mu = i / n, j = i - mu * n;
         const double v = src[mu * plane + j];
@@ -363,11 +366,13 @@ int u1_slab_select(double* theta_own, const double* ext_theta_own, size_t plane_
 }
 
 int u1_slab_select_state(double* state_own, const double* src_own, size_t plane_stride, double* theta_own, int Lx, int L,
-                         const int32_t* accept, u1_stream_t stream) {
+                         const int32_t* accept, double* sums_state, const double* sums_new, u1_stream_t stream) {
     g_launches = 0;
     if (!state_own || !src_own || !accept || Lx <= 0 || L <= 0 || plane_stride < (size_t)Lx * L) return U1_ERR_ARG;
+    if ((sums_state == nullptr) != (sums_new == nullptr)) return U1_ERR_ARG;
     const size_t n = (size_t)Lx * L;
-    k_slab_select_state<<<slab_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(state_own, src_own, plane_stride, n, theta_own, accept);
+    k_slab_select_state<<<slab_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(state_own, src_own, plane_stride, n, theta_own, accept,
+                                                                            sums_state, sums_new);
     count_launch();
     U1_CHECK_LAUNCH();
     return U1_OK;

@@ -246,10 +246,17 @@ class SlabHMC:
         self._st = torch.zeros(2, 2, Lxe, self.L, dtype=torch.float64, device=self._dev)
         self._state_ref = None                     # weakref to the caller's theta_own the state was taken from
         self._state_version = -1
-        self._sums6 = torch.zeros(6, dtype=torch.float64, device=self._dev)     # [old sums | new sums]
+        # [old sums | new sums]; old[0:2] (plaquette sums of the state) are carried from trajectory to trajectory by the
+        # select kernel, old[2] (sum pi^2) comes out of the momenta kernel: H_old costs no pass over the fields
+        self._sums6 = torch.zeros(6, dtype=torch.float64, device=self._dev)
+        self._sums_red = torch.zeros(6, dtype=torch.float64, device=self._dev)  # nccl transport: all-reduced copy
+        self._sums_valid = False                   # old[0:2] belong to the current state
         # private scratch for the sums kernels: a captured graph bakes this pointer in, so it must not be a
-        # shared grow-only cache entry
+        # shared grow-only cache entry.  _ws_m / _ws_d: single-launch reductions (zeroed ticket words)
         self._ws = torch.empty(4096 + 24 * (self.Lx + 2), dtype=torch.uint8, device=self._dev)
+        nred = int(self._lib.u1_slab_reduce_workspace_bytes(Lxe, self.L))
+        self._ws_m = torch.zeros(nred, dtype=torch.uint8, device=self._dev)
+        self._ws_d = torch.zeros(nred, dtype=torch.uint8, device=self._dev)
         self.peers: Optional[PeerRegions] = None
         self.peer_error: Optional[str] = None
         with torch.cuda.device(self._dev):
@@ -338,7 +345,7 @@ class SlabHMC:
         it is a different tensor than last time or torch has seen an in-place write to it since (tensor version
         counter).  After writing to theta_own through a raw pointer call invalidate_state()."""
         self._sync_state(theta_own)
-        if self._graph_mode and u is None and theta_own.is_cuda:
+        if self._graph_mode and u is None and theta_own.is_cuda and self._sums_valid:
             key = (theta_own.data_ptr(), tuple(theta_own.shape), torch.cuda.current_stream(self._dev).cuda_stream)
             g = self._graph
             if g is not None and g["key"] == key:
@@ -348,11 +355,14 @@ class SlabHMC:
                 if g is not None:
                     return self._replay(g)
         self._eager_calls += 1
+        if self._graph is not None:
+            self._graph["ctr"].add_(1)            # an eager trajectory between replays: keep the graph's device counter in step
         return self._trajectory_body(theta_own, u, self.traj_counter, None)
 
     def invalidate_state(self) -> None:
         """Forget the internal copy of the state: the next trajectory() copies theta_own in again."""
         self._state_ref = None
+        self._sums_valid = False
 
     def _sync_state(self, theta_own: torch.Tensor) -> None:
         ref = self._state_ref() if self._state_ref is not None else None
@@ -364,6 +374,7 @@ class SlabHMC:
                                                  stream_ptr(self._dev)), "u1_slab_copy_in")
         self._state_ref = weakref.ref(theta_own)
         self._state_version = theta_own._version
+        self._sums_valid = False                   # the next trajectory (eager) sums the new state's plaquettes itself
 
     def prepare_graph(self, theta_own: torch.Tensor) -> bool:
         """Capture the trajectory graph now (no replay).  trajectory() does this by itself on its third call; a
@@ -443,15 +454,24 @@ class SlabHMC:
             if side is not None:
                 side.wait_stream(main)
                 self._exchange(st, False, k, k, side.cuda_stream)
-            # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here)
-            self._call(lib.u1_momenta_rows_dev(st[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
-                                               Lx + 2 * k, L, L, sp), "u1_momenta_rows")
+            # momenta for own rows AND halo rows (global-site keyed: no exchange needed for pi here); sum pi^2 of the
+            # own rows -> s6[2]
+            self._call(lib.u1_momenta_rows_pi2_dev(st[1].data_ptr(), self.seed, self.chain, traj, ctr_p, self.x0 - k,
+                                                   Lx + 2 * k, L, L, k, Lx, s6[2:3].data_ptr(), self._ws_m.data_ptr(),
+                                                   self._ws_m.numel(), sp), "u1_momenta_rows_pi2")
             if side is not None:
                 main.wait_stream(side)
             else:
                 self._exchange(st, False, k, k, sp)          # theta halos
-            self._call(lib.u1_slab_sums_ext(st[0, 0, k].data_ptr(), st[1, 0, k].data_ptr(), plane,
-                                            s6[0:3].data_ptr(), Lx, L, ws, nb, sp), "u1_slab_sums_ext")
+            if not self._sums_valid:
+                # first trajectory after a copy-in: plaquette sums of the state (afterwards the select kernel carries them)
+                if ctr is not None:
+                    raise _lib.U1Error("slab graph capture needs valid state sums (run one eager trajectory first)")
+                tmp = torch.empty(3, dtype=torch.float64, device=dev)
+                self._call(lib.u1_slab_sums_ext(st[0, 0, k].data_ptr(), None, plane, tmp.data_ptr(), Lx, L, ws, nb, sp),
+                           "u1_slab_sums_ext")
+                s6[0:2].copy_(tmp[0:2])
+                self._sums_valid = True
             done = 0
             while done < self.n_steps:                       # blocks of <= k steps between halo exchanges
                 nblk = min(k, self.n_steps - done)
@@ -498,7 +518,8 @@ class SlabHMC:
             else:
                 self._exchange(cur, True, k, k, sp)
             self._call(lib.u1_slab_drift_sums_ext(cur[0, 0, k].data_ptr(), cur[1, 0, k].data_ptr(), plane,
-                                                  nxt[0, 0, k].data_ptr(), 0.5 * dt, s6[3:6].data_ptr(), Lx, L, ws, nb, sp),
+                                                  nxt[0, 0, k].data_ptr(), 0.5 * dt, s6[3:6].data_ptr(), Lx, L,
+                                                  self._ws_d.data_ptr(), self._ws_d.numel(), sp),
                        "u1_slab_drift_sums_ext")
             out = {n: torch.empty(1, dtype=torch.float64, device=dev) for n in ("dH", "H", "plaq", "topo")}
             out["accept"] = torch.empty(1, dtype=torch.int32, device=dev)
@@ -511,16 +532,19 @@ class SlabHMC:
                     out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(), out["plaq"].data_ptr(),
                     out["topo"].data_ptr(), sp), "u1_slab_metropolis_peer")
             else:
+                sr = self._sums_red                           # the local sums stay intact: old[0:2] are carried on
+                sr.copy_(s6)
                 if self.world > 1:
-                    dist.all_reduce(s6, group=self.group)
-                self._call(lib.u1_metropolis_sums_dev(s6[0:3].data_ptr(), s6[3:6].data_ptr(),
+                    dist.all_reduce(sr, group=self.group)
+                self._call(lib.u1_metropolis_sums_dev(sr[0:3].data_ptr(), sr[3:6].data_ptr(),
                                                       None if u_d is None else u_d.data_ptr(),
                                                       self.seed, self.chain, traj, ctr_p, 1, self.beta, float(L) * L,
                                                       out["dH"].data_ptr(), out["accept"].data_ptr(), out["H"].data_ptr(),
                                                       out["plaq"].data_ptr(), out["topo"].data_ptr(), sp),
                            "u1_metropolis_sums")
             self._call(lib.u1_slab_select_state(st[0, 0, k].data_ptr(), nxt[0, 0, k].data_ptr(), plane, theta_own.data_ptr(),
-                                                Lx, L, out["accept"].data_ptr(), sp), "u1_slab_select_state")
+                                                Lx, L, out["accept"].data_ptr(), s6[0:2].data_ptr(), s6[3:5].data_ptr(), sp),
+                       "u1_slab_select_state")
         if ctr is None:
             self.traj_counter += 1
         return out

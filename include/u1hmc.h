@@ -147,9 +147,14 @@ int u1_leapfrog_steps_rect3(const double* theta_in, const double* pi_in, double*
                             int* result_in_B, u1_stream_t stream);
 /* u1_slab_sums_ext of theta' = regularize(theta + a*pi) (hmc_u1.py:78-79 fused into the H_new reduction): theta' of
  * the own rows is written to theta_out_own (same plane stride, a different buffer), sums[0..2] as u1_slab_sums_ext.
- * theta AND pi of the row after the last own row are read in place (exchange one (theta, pi) row first). */
+ * theta AND pi of the row after the last own row are read in place (exchange one (theta, pi) row first).
+ * One launch: the block that finishes last adds the block partials in a fixed order.  ws: at least
+ * u1_slab_reduce_workspace_bytes(Lx, L) bytes whose first 256 bytes the caller ZEROED ONCE (ticket word; every launch
+ * leaves it zero again). */
 int u1_slab_drift_sums_ext(const double* theta_own, const double* pi_own, size_t plane_stride, double* theta_out_own,
                            double a, double* sums, int Lx, int L, void* ws, size_t ws_bytes, u1_stream_t stream);
+/* workspace of u1_slab_drift_sums_ext and u1_momenta_rows_pi2_dev for buffers of up to `rows` rows of L sites */
+size_t u1_slab_reduce_workspace_bytes(int rows, int L);
 /* One launch of the temporally blocked kernel restricted to tile rows [tile_row0, tile_row0 + tile_rows) of the
  * u1_leapfrog_multi_tile_rows(Lx) rows of 56-row tiles: ksteps <= 4 leapfrog steps (first drift first_drift, then
  * dt) from (theta_in, pi_in) to (theta_out, pi_out); a tile row reads rows [56 i - 4, 56 i + 60) (periodic) and
@@ -169,6 +174,12 @@ int u1_momenta_rows(double* pi, uint64_t seed, uint64_t chain, uint64_t traj,
  * itself increments, instead of a launch parameter frozen at capture time. */
 int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
                         long long x_first, int Lx, int L, int Lx_global, u1_stream_t stream);
+/* u1_momenta_rows_dev that also returns pi2_out[0] = sum of pi^2 over the rows [own_first, own_first + own_rows) of
+ * the buffer (the kinetic term of H_old, hmc_u1.py:86, without a second pass over pi).  ws as for
+ * u1_slab_drift_sums_ext (its own workspace: the two calls may be in flight on different streams). */
+int u1_momenta_rows_pi2_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,
+                            long long x_first, int Lx, int L, int Lx_global, int own_first, int own_rows, double* pi2_out,
+                            void* ws, size_t ws_bytes, u1_stream_t stream);
 /* out = regularize(theta + a*pi), elementwise over n doubles (last half drift, hmc_u1.py:78-79). */
 int u1_drift_wrap(const double* theta, const double* pi, double* out, double a, size_t n,
                   u1_stream_t stream);
@@ -248,9 +259,11 @@ int u1_slab_drift_wrap(double* ext_theta_own, const double* ext_pi_own, size_t p
                        u1_stream_t stream);
 int u1_slab_copy_in(const double* theta_own, double* ext_theta_own, size_t plane_stride, int Lx, int L, u1_stream_t stream);
 /* select into a state kept in extended layout: state_own = src_own where *accept != 0 (both plane-strided), and the
- * caller's contiguous theta_own [2][Lx][L] as well when it is not NULL. */
+ * caller's contiguous theta_own [2][Lx][L] as well when it is not NULL.  sums_state / sums_new (both or neither): on
+ * accept sums_state[0..1] = sums_new[0..1], i.e. the plaquette sums of the kept state travel with it, so the next
+ * trajectory's H_old needs no pass over theta. */
 int u1_slab_select_state(double* state_own, const double* src_own, size_t plane_stride, double* theta_own, int Lx, int L,
-                         const int32_t* accept, u1_stream_t stream);
+                         const int32_t* accept, double* sums_state, const double* sums_new, u1_stream_t stream);
 int u1_slab_select(double* theta_own, const double* ext_theta_own, size_t plane_stride, int Lx, int L,
                    const int32_t* accept, u1_stream_t stream);
 

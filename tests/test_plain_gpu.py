@@ -296,6 +296,84 @@ def test_multistep_kernel_bit_identical_to_single_steps(hb, Lx, L, B):
     assert torch.equal(res_t, c_t) and torch.equal(res_p, c_p)
 
 
+def test_slab_building_blocks_match_their_unfused_forms(hb):
+    """The fused entry points of the slab trajectory against the separate calls they replace, on a halo-extended
+    buffer (Lx own rows + k halo rows per side): u1_leapfrog_steps_rect3 (read-only input) == u1_leapfrog_steps_rect
+    bit for bit; u1_slab_drift_sums_ext == u1_slab_drift_wrap then u1_slab_sums_ext (theta' bit-identical, sums to
+    reduction round-off); u1_momenta_rows_pi2_dev == u1_momenta_rows_dev plus a sum over the own rows;
+    u1_slab_select_state copies state, caller copy and the carried sums on accept and nothing on reject."""
+    import ctypes as C
+    from hmc_ft_b200 import _lib
+    lib = _lib.load()
+    Lx, k, L, beta, dt = 120, 8, 512, 4.0, 0.07
+    Lxe = Lx + 2 * k
+    plane = Lxe * L
+    g = torch.Generator().manual_seed(5)
+    th = ((torch.rand(2, Lxe, L, generator=g, dtype=torch.float64) * 2 - 1) * 3).cuda()
+    pi = torch.randn(2, Lxe, L, generator=g, dtype=torch.float64).cuda()
+    sp = torch.cuda.current_stream().cuda_stream
+    # -- steps from a read-only input
+    a_t, a_p, b_t, b_p = th.clone(), pi.clone(), torch.empty_like(th), torch.empty_like(pi)
+    f1 = C.c_int(0)
+    _lib.check(lib.u1_leapfrog_steps_rect(a_t.data_ptr(), a_p.data_ptr(), b_t.data_ptr(), b_p.data_ptr(), 1, Lxe, L, beta,
+                                          0.5 * dt, dt, 6, C.byref(f1), sp))
+    want_t, want_p = (b_t, b_p) if f1.value else (a_t, a_p)
+    c_t, c_p, d_t, d_p = (torch.empty_like(th) for _ in range(4))
+    th0, pi0 = th.clone(), pi.clone()
+    f2 = C.c_int(0)
+    _lib.check(lib.u1_leapfrog_steps_rect3(th0.data_ptr(), pi0.data_ptr(), c_t.data_ptr(), c_p.data_ptr(), d_t.data_ptr(),
+                                           d_p.data_ptr(), 1, Lxe, L, beta, 0.5 * dt, dt, 6, C.byref(f2), sp))
+    got_t, got_p = (d_t, d_p) if f2.value else (c_t, c_p)
+    torch.cuda.synchronize()
+    assert torch.equal(got_t, want_t) and torch.equal(got_p, want_p)
+    assert torch.equal(th0, th) and torch.equal(pi0, pi)                       # input untouched
+    # -- final drift fused into the sums
+    nred = int(lib.u1_slab_reduce_workspace_bytes(Lxe, L))
+    ws_d = torch.zeros(nred, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(4096 + 24 * (Lx + 2), dtype=torch.uint8, device="cuda")
+    out_t = torch.zeros_like(th)
+    sums_f = torch.zeros(3, dtype=torch.float64, device="cuda")
+    for _ in range(2):                                                         # twice: the ticket word must reset itself
+        _lib.check(lib.u1_slab_drift_sums_ext(th[0, k].data_ptr(), pi[0, k].data_ptr(), plane, out_t[0, k].data_ptr(), 0.5 * dt,
+                                              sums_f.data_ptr(), Lx, L, ws_d.data_ptr(), ws_d.numel(), sp))
+    ref_t = th.clone()
+    # reference: drift the own rows AND the row below them (the fused kernel drifts that row in registers)
+    _lib.check(lib.u1_slab_drift_wrap(ref_t[0, k].data_ptr(), pi[0, k].data_ptr(), plane, Lx + 1, L, 0.5 * dt, sp))
+    sums_r = torch.zeros(3, dtype=torch.float64, device="cuda")
+    _lib.check(lib.u1_slab_sums_ext(ref_t[0, k].data_ptr(), pi[0, k].data_ptr(), plane, sums_r.data_ptr(), Lx, L,
+                                    ws.data_ptr(), ws.numel(), sp))
+    torch.cuda.synchronize()
+    assert torch.equal(out_t[:, k:k + Lx], ref_t[:, k:k + Lx])
+    assert torch.all(out_t[:, :k] == 0) and torch.all(out_t[:, k + Lx:] == 0)  # nothing written outside the own rows
+    assert rel(sums_f, sums_r) < 1e-13, (sums_f, sums_r)
+    # -- momenta with sum pi^2 of the own rows
+    ws_m = torch.zeros(nred, dtype=torch.uint8, device="cuda")
+    p1, p2 = torch.empty_like(pi), torch.empty_like(pi)
+    pi2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _lib.check(lib.u1_momenta_rows_dev(p1.data_ptr(), 11, 3, 5, None, 1000 - k, Lxe, L, 4096, sp))
+    for _ in range(2):
+        _lib.check(lib.u1_momenta_rows_pi2_dev(p2.data_ptr(), 11, 3, 5, None, 1000 - k, Lxe, L, 4096, k, Lx, pi2.data_ptr(),
+                                               ws_m.data_ptr(), ws_m.numel(), sp))
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2)
+    assert abs(pi2.item() - (p1[:, k:k + Lx] ** 2).sum().item()) < 1e-10 * pi2.item()
+    # -- select with carried sums
+    state = th.clone()
+    own = torch.zeros(2, Lx, L, dtype=torch.float64, device="cuda")
+    s_state = torch.tensor([1.0, 2.0], dtype=torch.float64, device="cuda")
+    s_new = torch.tensor([7.0, 8.0, 9.0], dtype=torch.float64, device="cuda")
+    for acc in (0, 1):
+        flag = torch.tensor([acc], dtype=torch.int32, device="cuda")
+        _lib.check(lib.u1_slab_select_state(state[0, k].data_ptr(), out_t[0, k].data_ptr(), plane, own.data_ptr(), Lx, L,
+                                            flag.data_ptr(), s_state.data_ptr(), s_new.data_ptr(), sp))
+        torch.cuda.synchronize()
+        if acc == 0:
+            assert torch.equal(state, th) and torch.all(own == 0) and s_state.tolist() == [1.0, 2.0]
+        else:
+            assert torch.equal(state[:, k:k + Lx], out_t[:, k:k + Lx]) and torch.equal(own, out_t[:, k:k + Lx])
+            assert torch.equal(state[:, :k], th[:, :k]) and s_state.tolist() == [7.0, 8.0]
+
+
 def test_full_size_size_independent_properties(hb):
     """BASELINE configs[1] shape (L=64, beta=6, 4096 chains): properties that need no oracle at this size.
     (1) the leapfrog map is reversible: integrate, flip the momenta, integrate again -> the start (mod 2 pi);
