@@ -1073,7 +1073,7 @@ using namespace u1;
 // ---------------------------------------------------------------------------------------
 // Host side: handle, workspace carving, orchestration
 // ---------------------------------------------------------------------------------------
-constexpr int kLanes = 2;      // internal streams of u1ft_trajectory
+constexpr int kLanes = 4;      // internal streams of u1ft_trajectory (at most)
 
 struct u1ft_handle_s {
     uint32_t magic;
@@ -1930,7 +1930,8 @@ int u1ft_trajectory(u1ft_handle_t h, double* theta, const double* pi_inject, con
     const size_t lane_bytes = carve_ft(nullptr, h->n_layers, Cmax, L, true).bytes;
     U1_TRY(check_ws_ft(ws, ws_bytes, (size_t)nlanes * lane_bytes));
     cudaStream_t user = (cudaStream_t)stream;
-    cudaStream_t lane_st[kLanes] = {user, user};
+    cudaStream_t lane_st[kLanes];
+    for (int l = 0; l < kLanes; ++l) lane_st[l] = user;
     if (nlanes > 1) {                                   // fork: lanes start after everything queued on `stream`
         U1_TRY(ensure_lanes(h));
         cudaError_t e = cudaEventRecord(h->ev_fork, user);
