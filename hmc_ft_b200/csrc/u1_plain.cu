@@ -440,153 +440,11 @@ k_leapfrog_multi(MultiArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// Thread-block-cluster form of the temporally blocked kernel: CY CTAs of one cluster sit side by side in y and
-// together hold a 64 x (32 CY) window; the column edges that the single-CTA kernel wraps around inside its own 32
-// columns cross to the neighbour CTA through distributed shared memory (st.shared::cluster into the neighbour's
-// edge slot), and the two barriers per step become cluster barriers (barrier.cluster arrive.release / wait.acquire)
-// with the plaquettes / kicks that need no neighbour value placed between arrive and wait.  Only the cluster window
-// wraps around, so the garbage ring costs 8 columns per 32 CY instead of 8 per 32: redundant work
-// 64*32CY / (56*(32CY-8)) = 1.22 (CY=4) or 1.18 (CY=8) instead of 1.52, HBM traffic 16.8 / 16.4 instead of 20.2 B per
-// site-update.  Same arithmetic per site, bit-identical to k_leapfrog_step.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned dsmem_addr(const void* local_smem, unsigned rank) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(local_smem), d;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(rank));
-    return d;
-}
-__device__ __forceinline__ void dsmem_store2(unsigned addr, double x, double y) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
-}
-
-template <int CY>
-__global__ void __launch_bounds__(256, 2)
-k_leapfrog_multi_cl(MultiArgs a) {
-    constexpr int L = kMsE, EW = 32, TX = 2, TY = 4, NTX = L / TX, NTY = EW / TY, OWC = CY * EW - 2 * kMsHalo;
-    extern __shared__ __align__(16) double dsm[];
-    double* colA = dsm;                          // [tx][ty] double2
-    double* rowA = colA + L * NTY;
-    double* colB = rowA + NTX * TY * NTY;
-    double* rowB = colB + L * NTY;
-    double* colAx = rowB + NTX * TY * NTY;       // [tx] double2: column 0 of the RIGHT neighbour CTA
-    double* colBx = colAx + L;                   // [tx] double2: last sin column of the LEFT neighbour CTA
-
-    const int tid = threadIdx.x, ty = tid % NTY, tx = tid / NTY;
-    const int x0 = tx * TX, y0 = ty * TY;
-    const int txD = (tx + 1) % NTX, txU = (tx + NTX - 1) % NTX;
-    const unsigned rk = cluster_rank();
-    const unsigned rkL = (rk + CY - 1) % CY, rkR = (rk + 1) % CY;
-    cluster_arrive();                            // every CTA of the cluster is resident before the first remote store
-    const int clusters_y = a.tiles_y;            // clusters per tile row
-    const int cidx = blockIdx.x / CY;
-    const int tile_xl = cidx / clusters_y, cl = cidx - tile_xl * clusters_y;
-    const int tile_x = a.tile_x0 + tile_xl;
-    const size_t V = (size_t)a.Lx * a.L;
-    const size_t base = (size_t)blockIdx.y * 2 * V;
-    int gy = cl * OWC - kMsHalo + (int)rk * EW + y0;
-    gy %= a.L; if (gy < 0) gy += a.L;
-    int gx[TX];
-#pragma unroll
-    for (int i = 0; i < TX; ++i) { int g = (tile_x * kMsOut - kMsHalo + x0 + i) % a.Lx; gx[i] = g < 0 ? g + a.Lx : g; }
-
-    double th0[TX][TY], th1[TX][TY], p0[TX][TY], p1[TX][TY];
-#pragma unroll
-    for (int i = 0; i < TX; ++i)
-#pragma unroll
-        for (int j = 0; j < TY; j += 2) {
-            const size_t g = base + (size_t)gx[i] * a.L + gy + j;
-            const double2 v0 = *reinterpret_cast<const double2*>(a.th + g);
-            const double2 v1 = *reinterpret_cast<const double2*>(a.th + g + V);
-            const double2 q0 = *reinterpret_cast<const double2*>(a.pi + g);
-            const double2 q1 = *reinterpret_cast<const double2*>(a.pi + g + V);
-            th0[i][j] = v0.x; th0[i][j + 1] = v0.y; th1[i][j] = v1.x; th1[i][j + 1] = v1.y;
-            p0[i][j] = q0.x; p0[i][j + 1] = q0.y; p1[i][j] = q1.x; p1[i][j + 1] = q1.y;
-        }
-    const unsigned remA = dsmem_addr(colAx + 2 * tx, rkL);      // my column 0 -> left neighbour's colAx[tx]
-    const unsigned remB = dsmem_addr(colBx + 2 * tx, rkR);      // my last sin column -> right neighbour's colBx[tx]
-    const double kb = a.dt * a.beta;
-    cluster_wait();
-    for (int s = 0; s < a.ksteps; ++s) {
-        const double dr = (s == 0) ? a.first_drift : a.dt;
-#pragma unroll
-        for (int i = 0; i < TX; ++i)
-#pragma unroll
-            for (int j = 0; j < TY; ++j) {
-                th0[i][j] = fma(dr, p0[i][j], th0[i][j]);
-                th1[i][j] = fma(dr, p1[i][j], th1[i][j]);
-            }
-        if (ty == 0) dsmem_store2(remA, th0[0][0], th0[1][0]);
-        else reinterpret_cast<double2*>(colA)[tx * NTY + ty] = make_double2(th0[0][0], th0[1][0]);
-        reinterpret_cast<double2*>(rowA)[(0 * NTX + tx) * NTY + ty] = make_double2(th1[0][0], th1[0][1]);
-        reinterpret_cast<double2*>(rowA)[(1 * NTX + tx) * NTY + ty] = make_double2(th1[0][2], th1[0][3]);
-        cluster_arrive();
-        double S[TX][TY];
-        // plaquettes that need no neighbour value: row 0, columns 0..2
-#pragma unroll
-        for (int j = 0; j + 1 < TY; ++j) S[0][j] = fast_sin(th0[0][j] - th1[0][j] - th0[0][j + 1] + th1[1][j]);
-        cluster_wait();
-        {
-            double rc[TX], rr[TY];
-            {
-                const double2 c = (ty == NTY - 1) ? reinterpret_cast<const double2*>(colAx)[tx]
-                                                  : reinterpret_cast<const double2*>(colA)[tx * NTY + ty + 1];
-                const double2 q0 = reinterpret_cast<const double2*>(rowA)[(0 * NTX + txD) * NTY + ty];
-                const double2 q1 = reinterpret_cast<const double2*>(rowA)[(1 * NTX + txD) * NTY + ty];
-                rc[0] = c.x; rc[1] = c.y; rr[0] = q0.x; rr[1] = q0.y; rr[2] = q1.x; rr[3] = q1.y;
-            }
-            S[0][TY - 1] = fast_sin(th0[0][TY - 1] - th1[0][TY - 1] - rc[0] + th1[1][TY - 1]);
-#pragma unroll
-            for (int j = 0; j < TY; ++j) {
-                const double right = (j + 1 < TY) ? th0[1][j + 1] : rc[1];
-                S[1][j] = fast_sin(th0[1][j] - th1[1][j] - right + rr[j]);
-            }
-        }
-        if (ty == NTY - 1) dsmem_store2(remB, S[0][TY - 1], S[1][TY - 1]);
-        else reinterpret_cast<double2*>(colB)[tx * NTY + ty] = make_double2(S[0][TY - 1], S[1][TY - 1]);
-        reinterpret_cast<double2*>(rowB)[(0 * NTX + tx) * NTY + ty] = make_double2(S[TX - 1][0], S[TX - 1][1]);
-        reinterpret_cast<double2*>(rowB)[(1 * NTX + tx) * NTY + ty] = make_double2(S[TX - 1][2], S[TX - 1][3]);
-        cluster_arrive();
-        // kicks that need no neighbour value: p0 columns 1..3, p1 row 1
-#pragma unroll
-        for (int i = 0; i < TX; ++i)
-#pragma unroll
-            for (int j = 1; j < TY; ++j) p0[i][j] = fma(-kb, S[i][j] - S[i][j - 1], p0[i][j]);
-#pragma unroll
-        for (int j = 0; j < TY; ++j) p1[1][j] = fma(-kb, S[0][j] - S[1][j], p1[1][j]);
-        cluster_wait();
-        {
-            const double2 c = (ty == 0) ? reinterpret_cast<const double2*>(colBx)[tx]
-                                        : reinterpret_cast<const double2*>(colB)[tx * NTY + ty - 1];
-            const double2 q0 = reinterpret_cast<const double2*>(rowB)[(0 * NTX + txU) * NTY + ty];
-            const double2 q1 = reinterpret_cast<const double2*>(rowB)[(1 * NTX + txU) * NTY + ty];
-            p0[0][0] = fma(-kb, S[0][0] - c.x, p0[0][0]);
-            p0[1][0] = fma(-kb, S[1][0] - c.y, p0[1][0]);
-            p1[0][0] = fma(-kb, q0.x - S[0][0], p1[0][0]);
-            p1[0][1] = fma(-kb, q0.y - S[0][1], p1[0][1]);
-            p1[0][2] = fma(-kb, q1.x - S[0][2], p1[0][2]);
-            p1[0][3] = fma(-kb, q1.y - S[0][3], p1[0][3]);
-        }
-    }
-    // write back the inner block of the cluster window (clipped to the lattice for the last tile row / cluster)
-    const int ly = (int)rk * EW + y0 - kMsHalo;        // column inside the cluster's inner block (multiple of 4)
-    if (ly < 0 || ly >= OWC || cl * OWC + ly >= a.L) return;
-#pragma unroll
-    for (int i = 0; i < TX; ++i) {
-        const int lx = x0 + i - kMsHalo;
-        if (lx < 0 || lx >= kMsOut || tile_x * kMsOut + lx >= a.Lx) continue;
-#pragma unroll
-        for (int j = 0; j < TY; j += 2) {
-            const size_t g = base + (size_t)gx[i] * a.L + gy + j;
-            *reinterpret_cast<double2*>(a.tho + g) = make_double2(th0[i][j], th0[i][j + 1]);
-            *reinterpret_cast<double2*>(a.tho + g + V) = make_double2(th1[i][j], th1[i][j + 1]);
-            *reinterpret_cast<double2*>(a.pio + g) = make_double2(p0[i][j], p0[i][j + 1]);
-            *reinterpret_cast<double2*>(a.pio + g + V) = make_double2(p1[i][j], p1[i][j + 1]);
-        }
-    }
-}
+// Measured and rejected in round 2 (profiles/r02_multistep_cluster_dsmem_variant.log, commit c0f5151 has the code): a
+// thread-block-cluster form (2/4/8 CTAs side by side share one 64 x 32CY window, column edges pushed into the neighbour
+// CTA through distributed shared memory, barrier.cluster arrive/wait with the neighbour-independent work in between).
+// Bit-identical and 1.31/1.22/1.18x instead of 1.52x redundant halo work, but 462/486/537 us per 4 steps at L=4096
+// against 307 us: each cluster barrier costs ~0.6 us of arrival skew between CTAs on different SMs.
 
 // SM count of the current device (cached per device)
 static int sm_count() {
@@ -612,9 +470,8 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
     MultiArgs a{};
     a.th = th; a.pi = pi; a.tho = tho; a.pio = pio;
     a.Lx = Lx; a.L = L; a.ksteps = ksteps; a.beta = beta; a.first_drift = first_drift; a.dt = dt;
-    static int ew = 0, cl = -1;
+    static int ew = 0;
     if (ew == 0) { const char* e = getenv("U1_MULTISTEP_EW"); ew = (e && atoi(e) == 64) ? 64 : 32; }
-    if (cl < 0) { const char* e = getenv("U1_MULTISTEP_CL"); cl = e ? atoi(e) : 0; }      // thread-block cluster size in y (0: none)
     const int tiles_all = (Lx + kMsOut - 1) / kMsOut;
     if (tile_rows < 0) tile_rows = tiles_all - tile_row0;
     if (tile_row0 < 0 || tile_rows < 1 || tile_row0 + tile_rows > tiles_all) return U1_ERR_ARG;
@@ -640,31 +497,6 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
             k_leapfrog_multi<64><<<dim3(tiles_x * a.tiles_y, nb), 512, smem, st>>>(s);
             count_launch();
             U1_CHECK_LAUNCH();
-        }
-    } else if (cl == 2 || cl == 4 || cl == 8) {
-        constexpr int NTY = 8;
-        constexpr size_t smem = (size_t)(2 * (kMsE * NTY + NTX * 4 * NTY) + 2 * kMsE) * sizeof(double);
-        const int owc = cl * 32 - 2 * kMsHalo;
-        a.tiles_y = (L + owc - 1) / owc;                     // clusters per tile row
-        for (int b0 = 0; b0 < B; b0 += kMaxGridY) {
-            const int nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
-            MultiArgs s = a;
-            const size_t off = (size_t)b0 * 2 * Lx * L;
-            s.th += off; s.pi += off; s.tho += off; s.pio += off;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(tiles_x * a.tiles_y * cl, nb);
-            cfg.blockDim = dim3(256);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaError_t e = (cl == 2) ? cudaLaunchKernelEx(&cfg, k_leapfrog_multi_cl<2>, s)
-                          : (cl == 4) ? cudaLaunchKernelEx(&cfg, k_leapfrog_multi_cl<4>, s)
-                                      : cudaLaunchKernelEx(&cfg, k_leapfrog_multi_cl<8>, s);
-            count_launch();
-            if (e != cudaSuccess) return (int)e;
         }
     } else {
         constexpr int NTY = 8;
@@ -1774,9 +1606,6 @@ int u1_plain_preload_slab_kernels(void) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<32>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi<64>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi_cl<2>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi_cl<4>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_multi_cl<8>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_leapfrog_step<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_partial_sums);
