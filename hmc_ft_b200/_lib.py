@@ -38,6 +38,7 @@ SIGNATURES = {
     "u1_slab_drift_sums_ext": (_i, [_vp, _vp, _sz, _vp, _d, _vp, _i, _i, _vp, _sz, _vp]),
     "u1_leapfrog_multi_tile_rows": (_i, [_i]),
     "u1_leapfrog_multi_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _i, _vp]),
+    "u1_leapfrog_multi_rows2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _i, _i, _i, _vp]),
     "u1_momenta_rows": (_i, [_vp, _u64, _u64, _u64, C.c_longlong, _i, _i, _i, _vp]),
     "u1_momenta_rows_dev": (_i, [_vp, _u64, _u64, _u64, _vp, C.c_longlong, _i, _i, _i, _vp]),
     "u1_drift_wrap": (_i, [_vp, _vp, _vp, _d, _sz, _vp]),

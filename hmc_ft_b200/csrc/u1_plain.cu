@@ -321,6 +321,7 @@ struct MultiArgs {
     double* tho; double* pio;
     int Lx, L, tiles_y, ksteps;
     int tile_x0;          // first tile row of this launch (launches may cover a sub-range of tile rows)
+    int split_rows, split_jump;   // tile rows >= split_rows of the launch are shifted by split_jump (two ranges in one launch)
     double beta, first_drift, dt;
 };
 
@@ -347,7 +348,7 @@ k_leapfrog_multi(MultiArgs a) {
     const size_t V = (size_t)a.Lx * a.L;
     const double kb = a.dt * a.beta;
     const int tile_xl = blockIdx.x / a.tiles_y, tile_y = blockIdx.x - tile_xl * a.tiles_y;
-    const int tile_x = a.tile_x0 + tile_xl;
+    const int tile_x = a.tile_x0 + tile_xl + (tile_xl >= a.split_rows ? a.split_jump : 0);
     const size_t base = (size_t)blockIdx.y * 2 * V;
     // global coordinates of this thread's 2 x 4 sites (periodic)
     int gy = tile_y * OW - kMsHalo + y0;
@@ -466,7 +467,7 @@ static bool multi_supported(int Lx, int L) {
 
 static int launch_multi(const double* th, const double* pi, double* tho, double* pio, int B, int Lx, int L,
                         double beta, double first_drift, double dt, int ksteps, cudaStream_t st,
-                        int tile_row0 = 0, int tile_rows = -1) {
+                        int tile_row0 = 0, int tile_rows = -1, int tile_row1 = 0, int tile_rows1 = 0) {
     MultiArgs a{};
     a.th = th; a.pi = pi; a.tho = tho; a.pio = pio;
     a.Lx = Lx; a.L = L; a.ksteps = ksteps; a.beta = beta; a.first_drift = first_drift; a.dt = dt;
@@ -475,8 +476,11 @@ static int launch_multi(const double* th, const double* pi, double* tho, double*
     const int tiles_all = (Lx + kMsOut - 1) / kMsOut;
     if (tile_rows < 0) tile_rows = tiles_all - tile_row0;
     if (tile_row0 < 0 || tile_rows < 1 || tile_row0 + tile_rows > tiles_all) return U1_ERR_ARG;
+    if (tile_rows1 < 0 || (tile_rows1 > 0 && (tile_row1 < tile_row0 + tile_rows || tile_row1 + tile_rows1 > tiles_all))) return U1_ERR_ARG;
     a.tile_x0 = tile_row0;
-    const int tiles_x = tile_rows;
+    a.split_rows = tile_rows;                                  // second range [tile_row1, tile_row1 + tile_rows1) follows the first
+    a.split_jump = tile_rows1 > 0 ? tile_row1 - (tile_row0 + tile_rows) : 0;
+    const int tiles_x = tile_rows + tile_rows1;
     constexpr int NTX = kMsE / 2;
     if (ew == 64) {
         constexpr int NTY = 16;
@@ -1409,6 +1413,18 @@ int u1_leapfrog_multi_rows(const double* theta_in, const double* pi_in, double* 
     if (!multi_supported(Lx, L)) return U1_ERR_UNSUPPORTED;
     return launch_multi(theta_in, pi_in, theta_out, pi_out, 1, Lx, L, beta, first_drift, dt, ksteps, (cudaStream_t)stream,
                         tile_row0, tile_rows);
+}
+
+int u1_leapfrog_multi_rows2(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                            int Lx, int L, double beta, double first_drift, double dt, int ksteps,
+                            int tile_row0, int tile_rows, int tile_row1, int tile_rows1, u1_stream_t stream) {
+    g_launches = 0;
+    if (!theta_in || !pi_in || !theta_out || !pi_out || Lx <= 0 || L <= 0) return U1_ERR_ARG;
+    if (theta_in == theta_out || pi_in == pi_out || ksteps < 1 || ksteps > kMsHalo) return U1_ERR_ARG;
+    if (!aligned16(theta_in) || !aligned16(pi_in) || !aligned16(theta_out) || !aligned16(pi_out)) return U1_ERR_ARG;
+    if (!multi_supported(Lx, L)) return U1_ERR_UNSUPPORTED;
+    return launch_multi(theta_in, pi_in, theta_out, pi_out, 1, Lx, L, beta, first_drift, dt, ksteps, (cudaStream_t)stream,
+                        tile_row0, tile_rows, tile_row1, tile_rows1);
 }
 
 int u1_momenta_rows_dev(double* pi, uint64_t seed, uint64_t chain, uint64_t traj, const uint64_t* traj_dev,

@@ -487,9 +487,11 @@ class SlabHMC:
                             self.beta, dt, dt, first)
                     self._call(lib.u1_leapfrog_multi_rows(*args, i0, i1 - i0, sp), "u1_leapfrog_multi_rows")
                     main.wait_stream(side)
-                    if i0 > 0:
+                    if i0 > 0 and T > i1:                    # top and bottom boundary tile rows in one launch
+                        self._call(lib.u1_leapfrog_multi_rows2(*args, 0, i0, i1, T - i1, sp), "u1_leapfrog_multi_rows2")
+                    elif i0 > 0:
                         self._call(lib.u1_leapfrog_multi_rows(*args, 0, i0, sp), "u1_leapfrog_multi_rows")
-                    if T > i1:
+                    elif T > i1:
                         self._call(lib.u1_leapfrog_multi_rows(*args, i1, T - i1, sp), "u1_leapfrog_multi_rows")
                     cur, nxt = nxt, cur
                 elif done > 0:

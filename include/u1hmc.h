@@ -164,6 +164,11 @@ int u1_leapfrog_multi_tile_rows(int Lx);
 int u1_leapfrog_multi_rows(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
                            int Lx, int L, double beta, double first_drift, double dt, int ksteps,
                            int tile_row0, int tile_rows, u1_stream_t stream);
+/* Same for TWO disjoint ranges of tile rows in one launch: [tile_row0, +tile_rows) and [tile_row1, +tile_rows1) with
+ * tile_row1 >= tile_row0 + tile_rows (the slab path finishes the top and the bottom boundary tile rows together). */
+int u1_leapfrog_multi_rows2(const double* theta_in, const double* pi_in, double* theta_out, double* pi_out,
+                            int Lx, int L, double beta, double first_drift, double dt, int ksteps,
+                            int tile_row0, int tile_rows, int tile_row1, int tile_rows1, u1_stream_t stream);
 /* Philox momenta for rows x_first .. x_first+Lx-1 (taken modulo Lx_global) of ONE global lattice of
  * Lx_global x L sites: pi[2][Lx][L].  Keyed by the global site index, so the field does not depend
  * on the decomposition. */
