@@ -702,6 +702,115 @@ k_final_update(const __grid_constant__ ConvP<kW, kActCh> p, const double* __rest
     }
 }
 
+// k_final_update with the input staged like k_conv_tile (L in {32, 64, 128}): the CTA owns 4*128/LL lattice rows, i.e.
+// 128 active sites, one per thread; per input channel the rows (plus one halo row above and below) come in by cp.async
+// through the 3-deep ring, so the nine window reads per channel are LDS instead of dependent global loads (ncu of the
+// direct-load form: long_scoreboard 6.0 of 11 stall cycles per issue, 75 us at 342 chains for 30 us of HBM traffic).
+// Same arithmetic in the same order as k_final_update.
+template <int LL>
+__global__ void __launch_bounds__(kConvThreads)
+k_final_update_tile(const __grid_constant__ ConvP<kW, kActCh> p, const double* __restrict__ in,
+                    const double* __restrict__ th, double* __restrict__ th_out,
+                    double* __restrict__ Kout, double* __restrict__ dout, double* __restrict__ partial,
+                    const double* __restrict__ gelu_tab, int k) {
+    constexpr int TP = kConvThreads / LL, NR = 4 * TP, TROWS = NR + 2, TILE = TROWS * LL, V = LL * LL, HC = LL / 2;
+    constexpr int NBLK = LL / NR;                       // CTAs per chain
+    extern __shared__ __align__(16) double s_dyn[];
+    __shared__ double red[32];
+    double* tile = s_dyn;                               // [kTileStages][TILE]
+    double* s_tab = s_dyn + kTileStages * TILE;
+    asm volatile("griddepcontrol.launch_dependents;");
+    for (int i = 2 * threadIdx.x; i < kGeluTableDoubles; i += 2 * kConvThreads) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_tab + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gelu_tab + i));
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / NBLK, R0 = (blockIdx.x - b * NBLK) * NR;
+    const Subset ss = subset_of(k);
+    const int ar = tid / HC, ac = tid - ar * HC;
+    const int x = R0 + 2 * ar + ss.a, y = 2 * ac + ss.b;
+    const double* ib = in + (size_t)b * kW * V;
+    auto issue = [&](int c, int stage) {
+        const double* pc = ib + (size_t)c * V;
+        constexpr int CHUNKS = TILE / 2;
+        for (int q = tid; q < CHUNKS; q += kConvThreads) {
+            const int r = (2 * q) / LL, col = 2 * q - r * LL;
+            int xx = R0 - 1 + r;
+            xx = xx < 0 ? xx + LL : (xx >= LL ? xx - LL : xx);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + stage * TILE + r * LL + col);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pc + xx * LL + col));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+#pragma unroll
+    for (int st = 0; st < kTileStages - 1; ++st) issue(st, st);
+    const int ym = (y == 0 ? LL - 1 : y - 1), yp = (y == LL - 1 ? 0 : y + 1);
+    const int tr = x - R0;                              // tile rows tr, tr+1, tr+2 = lattice rows x-1, x, x+1
+    // theta of the 2x2 block and the six angles while the first tiles are in flight
+    const double* t0 = th + (size_t)b * 2 * V;
+    Lat g{t0, t0 + V, LL};
+    LinkTerms lt;
+    link_terms(g, ss.mu, x, y, lt);
+    const int r = x * LL + y;
+    const int xo = (x ^ 1) * LL, yo = y ^ 1;
+    const int site[4] = {r, x * LL + yo, xo + y, xo + yo};
+    double o0v[4], o1v[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { o0v[m] = t0[site[m]]; o1v[m] = t0[V + site[m]]; }
+    double acc[kActCh];
+#pragma unroll
+    for (int j = 0; j < kActCh; ++j) acc[j] = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < kW; ++c) {
+        if (c + kTileStages - 1 <= kW) asm volatile("cp.async.wait_group %0;" ::"n"(kTileStages - 2));
+        else asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        if (c + kTileStages - 1 < kW) issue(c + kTileStages - 1, (c + kTileStages - 1) % kTileStages);
+        const double* t = tile + (c % kTileStages) * TILE;
+        double v[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            v[i * 3 + 0] = t[(tr + i) * LL + ym];
+            v[i * 3 + 1] = t[(tr + i) * LL + y];
+            v[i * 3 + 2] = t[(tr + i) * LL + yp];
+        }
+        const double* w = p.w + c * 9 * kActCh;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+            for (int j = 0; j < kActCh; ++j) acc[j] = fma(w[tp * kActCh + j], v[tp], acc[j]);
+    }
+    const size_t ob = (size_t)b * kW * V + r;
+    double d[6], jj[6];
+#pragma unroll
+    for (int j = 0; j < kActCh; ++j) {
+        double gg, dd;
+        gelu_and_grad(s_tab, acc[j] + p.b[j], gg, dd);
+        const double kq = atan(gg) / kPi / 2;                               // cnn_model_opt.py:46
+        if (dout) {
+            const size_t idx = ob + (size_t)term_channel(ss.mu, j) * V;
+            Kout[idx] = kq;
+            dout[idx] = dd / ((1.0 + gg * gg) * kTwoPi);
+        }
+        double sn, cs;
+        fast_sincos(lt.A[j], sn, cs);
+        d[j] = kq * (term_sign(ss.mu, j) * sn);
+        jj[j] = kq * (-cs);
+    }
+    const double delta = (d[0] + d[1]) + (((d[2] + d[3]) + d[4]) + d[5]);
+    const double jac = (jj[0] + jj[1]) + (((jj[2] + jj[3]) + jj[4]) + jj[5]);
+    double ld[1] = {log(1.0 + jac)};
+    double* o0 = th_out + (size_t)b * 2 * V;
+    if (ss.mu == 0) o0v[0] += delta; else o1v[0] += delta;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { o0[site[m]] = o0v[m]; o0[V + site[m]] = o1v[m]; }
+    if (partial) {
+        block_sum<1>(ld, red);
+        if (threadIdx.x == 0) partial[(size_t)b * NBLK + (blockIdx.x - b * NBLK)] = ld[0];
+    }
+}
+
 // One fixed-point iteration of the inverse transformation (field_trans_opt.py:245-282):
 // next = curr - ft_phase(iter); per-block partial sums of |next-iter|^2 and |iter|^2.
 __global__ void __launch_bounds__(kUpdThreads)
@@ -824,7 +933,8 @@ k_ft_update_bwd(const double* __restrict__ th, const double* __restrict__ K,
 // k_ft_update_bwd does and park it in shared memory; the TAX*H owner threads also write AP / AR.  After the barrier
 // the owner threads run the transposed final convolution of their 2x2 output block from the four zbar entries in
 // shared memory - same operations in the same order as k_conv_final_bwd_sparse, so the result is bit-identical -
-// and zbar itself never goes to memory.  H in {16, 32, 64}.
+// and zbar itself never goes to memory.  H in {16, 32, 64}.  (Two passes of six output channels with the GELU' factors
+// requested ahead of the FMAs were measured slower: 165 vs 112 us at 342 chains, profiles/r02_ft_fusion_ab.log.)
 template <int H>
 __global__ void __launch_bounds__(kConvThreads + H)
 k_final_bwd_fused(const __grid_constant__ ConvP<kW, kW> pT, const double* __restrict__ th, const double* __restrict__ K,
@@ -1439,7 +1549,16 @@ static int ft_forward_chunk(u1ft_handle_t h, const FtWs& w, int C, int L, bool s
             const double* in = w.A;
             const double* th = w.th[k];
             double* dfin = store ? Dbuf(w, h->n_layers, C, L, k, h->n_layers - 1) : nullptr;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, k_final_update, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k, L);
+            cudaError_t e;
+            if (tile_path_enabled() > 1 && (L == 32 || L == 64 || L == 128)) {
+                const int tp = kConvThreads / L;
+                cfg.dynamicSmemBytes = ((size_t)kTileStages * (4 * tp + 2) * L + kGeluTableDoubles) * sizeof(double);
+                if (L == 32) e = cudaLaunchKernelEx(&cfg, k_final_update_tile<32>, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k);
+                else if (L == 64) e = cudaLaunchKernelEx(&cfg, k_final_update_tile<64>, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k);
+                else e = cudaLaunchKernelEx(&cfg, k_final_update_tile<128>, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k);
+            } else {
+                e = cudaLaunchKernelEx(&cfg, k_final_update, h->fs[k], in, th, w.th[k + 1], w.Kk[k], dfin, part, tab, k, L);
+            }
             count_launch();
             if (e != cudaSuccess) return (int)e;
         } else {

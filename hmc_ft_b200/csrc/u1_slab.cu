@@ -66,6 +66,7 @@ struct XchArgs {
 };
 
 constexpr int kXchThreads = 256;
+constexpr int kXchUnroll = 4;
 
 __global__ void __launch_bounds__(kXchThreads) k_slab_exchange(XchArgs a) {
     __shared__ unsigned long long s_epoch;
@@ -84,18 +85,31 @@ __global__ void __launch_bounds__(kXchThreads) k_slab_exchange(XchArgs a) {
     double* st_up = reinterpret_cast<double*>(reinterpret_cast<char*>(a.up) + kPeerStageOff) + ((size_t)par * 2 + 1) * side;   // up's bottom-in
     double* st_dn = reinterpret_cast<double*>(reinterpret_cast<char*>(a.dn) + kPeerStageOff) + ((size_t)par * 2 + 0) * side;   // dn's top-in
     // ---- push: my first rows_up rows -> up ; my last rows_dn rows -> dn ----
+    // (kXchUnroll independent 16-byte loads in flight per thread before the first store: the copy is latency-bound)
     const long long n_up = (long long)nplanes * a.rows_up * L2, n_dn = (long long)nplanes * a.rows_dn * L2;
-    for (long long i = blockIdx.x * (long long)kXchThreads + tid; i < n_up + n_dn; i += (long long)gridDim.x * kXchThreads) {
-        const bool to_up = i < n_up;
-        const long long j = to_up ? i : i - n_up;
-        const int rows = to_up ? a.rows_up : a.rows_dn;
-        const int p = (int)(j / ((long long)rows * L2));
-        const int rem = (int)(j - (long long)p * rows * L2);
-        const int r = rem / L2, c = (rem - r * L2) << 1;
-        const int row = to_up ? (k + r) : (Lx + k - rows + r);
-        const double2 v = *reinterpret_cast<const double2*>(src_plane(p) + (size_t)row * L + c);
-        double* dst = (to_up ? st_up : st_dn) + ((size_t)p * k + r) * L + c;
-        *reinterpret_cast<double2*>(dst) = v;                       // 16-byte store over NVLink
+    const long long stride = (long long)gridDim.x * kXchThreads;
+    for (long long i0 = blockIdx.x * (long long)kXchThreads + tid; i0 < n_up + n_dn; i0 += stride * kXchUnroll) {
+        double2 v[kXchUnroll];
+        double* dst[kXchUnroll];
+#pragma unroll
+        for (int u = 0; u < kXchUnroll; ++u) {
+            const long long i = i0 + u * stride;
+            dst[u] = nullptr;
+            if (i < n_up + n_dn) {
+                const bool to_up = i < n_up;
+                const long long j = to_up ? i : i - n_up;
+                const int rows = to_up ? a.rows_up : a.rows_dn;
+                const int p = (int)(j / ((long long)rows * L2));
+                const int rem = (int)(j - (long long)p * rows * L2);
+                const int r = rem / L2, c = (rem - r * L2) << 1;
+                const int row = to_up ? (k + r) : (Lx + k - rows + r);
+                v[u] = *reinterpret_cast<const double2*>(src_plane(p) + (size_t)row * L + c);
+                dst[u] = (to_up ? st_up : st_dn) + ((size_t)p * k + r) * L + c;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kXchUnroll; ++u)
+            if (dst[u]) *reinterpret_cast<double2*>(dst[u]) = v[u];             // 16-byte store over NVLink
     }
     __syncthreads();
     if (tid == 0) {
@@ -120,16 +134,28 @@ __global__ void __launch_bounds__(kXchThreads) k_slab_exchange(XchArgs a) {
     const double* in_bot = in_top + side;
     const long long m_top = (long long)nplanes * a.rows_dn * L2, m_bot = (long long)nplanes * a.rows_up * L2;
     if (s_ok) {
-        for (long long i = blockIdx.x * (long long)kXchThreads + tid; i < m_top + m_bot; i += (long long)gridDim.x * kXchThreads) {
-            const bool top = i < m_top;
-            const long long j = top ? i : i - m_top;
-            const int rows = top ? a.rows_dn : a.rows_up;
-            const int p = (int)(j / ((long long)rows * L2));
-            const int rem = (int)(j - (long long)p * rows * L2);
-            const int r = rem / L2, c = (rem - r * L2) << 1;
-            const int row = top ? (k - rows + r) : (Lx + k + r);
-            const double2 v = *reinterpret_cast<const double2*>((top ? in_top : in_bot) + ((size_t)p * k + r) * L + c);
-            *reinterpret_cast<double2*>(src_plane(p) + (size_t)row * L + c) = v;
+        for (long long i0 = blockIdx.x * (long long)kXchThreads + tid; i0 < m_top + m_bot; i0 += stride * kXchUnroll) {
+            double2 v[kXchUnroll];
+            double* dst[kXchUnroll];
+#pragma unroll
+            for (int u = 0; u < kXchUnroll; ++u) {
+                const long long i = i0 + u * stride;
+                dst[u] = nullptr;
+                if (i < m_top + m_bot) {
+                    const bool top = i < m_top;
+                    const long long j = top ? i : i - m_top;
+                    const int rows = top ? a.rows_dn : a.rows_up;
+                    const int p = (int)(j / ((long long)rows * L2));
+                    const int rem = (int)(j - (long long)p * rows * L2);
+                    const int r = rem / L2, c = (rem - r * L2) << 1;
+                    const int row = top ? (k - rows + r) : (Lx + k + r);
+                    v[u] = *reinterpret_cast<const double2*>((top ? in_top : in_bot) + ((size_t)p * k + r) * L + c);
+                    dst[u] = src_plane(p) + (size_t)row * L + c;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kXchUnroll; ++u)
+                if (dst[u]) *reinterpret_cast<double2*>(dst[u]) = v[u];
         }
     }
     __syncthreads();

@@ -68,3 +68,22 @@ def test_halo_exchange_world1():
     ext[:, k:k + Lx] = torch.arange(Lx, dtype=torch.float64)[None, :, None] + 1
     HaloExchanger(Lx, k).exchange(ext)
     assert ext[0, :, 0].tolist() == [4, 5, 1, 2, 3, 4, 5, 1, 2]
+
+
+def test_slab_halo_cost_model():
+    """SlabHMC._choose_halo (host logic, no GPU): halo widths are multiples of 4 (steps per launch of the temporally blocked
+    kernel), never exceed the slab or the trajectory, and at the 8-GPU shape of BASELINE configs[4] (512 rows per rank, 50
+    steps) the model picks a width whose extended slab is exactly 10 tile rows of 56 (the minimum of the 8-GPU sweep in
+    profiles/r02_slab_8gpu_halo_sweep.json: 20-24)."""
+    from hmc_ft_b200.sharding import SlabHMC
+
+    def choose(Lx, n):
+        s = SlabHMC.__new__(SlabHMC)
+        s.Lx, s.n_steps = Lx, n
+        return s._choose_halo()
+
+    for Lx, n in [(512, 50), (1024, 50), (2048, 50), (4096, 50), (64, 9), (512, 10), (512, 4)]:
+        k = choose(Lx, n)
+        assert k % 4 == 0 and 4 <= k <= 32 and k <= Lx and k <= max(4, n)
+    k = choose(512, 50)
+    assert k in (20, 24) and -(-(512 + 2 * k) // 56) == 10
