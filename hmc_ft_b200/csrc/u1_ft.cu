@@ -986,37 +986,46 @@ k_final_bwd_fused(const __grid_constant__ ConvP<kW, kW> pT, const double* __rest
     if (!owner) return;
     const int yb = (ya + 1 == H) ? 0 : ya + 1;
     const int X1 = wrapi(X0 + 1, L), Y1 = wrapi(Y0 + 1, L);
-    double a00[kW], a01[kW], a10[kW], a11[kW];
+    // the 24 zbar values of this 2x2 block in registers, then one rolled loop over the 12 output channels: 54 FMAs per
+    // channel against constant-bank weights indexed by the channel counter, the four GELU' factors of the NEXT channel
+    // requested before the FMAs of the current one (few registers, so many CTAs per SM hide the store latency).
+    // Per accumulator the j = 0..5 order is that of k_conv_final_bwd_sparse: bit-identical.
+    double z00[kActCh], z01[kActCh], z10[kActCh], z11[kActCh];
 #pragma unroll
-    for (int c = 0; c < kW; ++c) { a00[c] = 0.0; a01[c] = 0.0; a10[c] = 0.0; a11[c] = 0.0; }
-#pragma unroll 1
     for (int j = 0; j < kActCh; ++j) {
-        const int o = term_channel(ss.mu, j);
-        const double z00 = zs[j][rx * H + ya], z01 = zs[j][rx * H + yb];
-        const double z10 = zs[j][(rx + 1) * H + ya], z11 = zs[j][(rx + 1) * H + yb];
-        const double* w = pT.w + o * 9 * kW;          // w[tap'*12 + c], tap' = position of the source relative to the site
-#pragma unroll
-        for (int c = 0; c < kW; ++c) {
-            a00[c] = fma(w[4 * kW + c], z00, a00[c]);
-            a01[c] = fma(w[3 * kW + c], z00, a01[c]);
-            a01[c] = fma(w[5 * kW + c], z01, a01[c]);
-            a10[c] = fma(w[1 * kW + c], z00, a10[c]);
-            a10[c] = fma(w[7 * kW + c], z10, a10[c]);
-            a11[c] = fma(w[0 * kW + c], z00, a11[c]);
-            a11[c] = fma(w[2 * kW + c], z01, a11[c]);
-            a11[c] = fma(w[6 * kW + c], z10, a11[c]);
-            a11[c] = fma(w[8 * kW + c], z11, a11[c]);
-        }
+        z00[j] = zs[j][rx * H + ya];       z01[j] = zs[j][rx * H + yb];
+        z10[j] = zs[j][(rx + 1) * H + ya]; z11[j] = zs[j][(rx + 1) * H + yb];
     }
     const size_t ob = (size_t)b * kW * V;
     const int s00 = X0 * L + Y0, s01 = X0 * L + Y1, s10 = X1 * L + Y0, s11 = X1 * L + Y1;
+    int oc[kActCh];
 #pragma unroll
+    for (int j = 0; j < kActCh; ++j) oc[j] = term_channel(ss.mu, j) * 9 * kW;
+    double m00 = mul[ob + s00], m01 = mul[ob + s01], m10 = mul[ob + s10], m11 = mul[ob + s11];
+#pragma unroll 1
     for (int c = 0; c < kW; ++c) {
         const size_t cb = ob + (size_t)c * V;
-        out[cb + s00] = a00[c] * mul[cb + s00];
-        out[cb + s01] = a01[c] * mul[cb + s01];
-        out[cb + s10] = a10[c] * mul[cb + s10];
-        out[cb + s11] = a11[c] * mul[cb + s11];
+        double n00 = 0.0, n01 = 0.0, n10 = 0.0, n11 = 0.0;
+        if (c + 1 < kW) { n00 = mul[cb + V + s00]; n01 = mul[cb + V + s01]; n10 = mul[cb + V + s10]; n11 = mul[cb + V + s11]; }
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll
+        for (int j = 0; j < kActCh; ++j) {
+            const double* w = pT.w + oc[j] + c;           // w[tap'*12 + c], tap' = position of the source relative to the site
+            a00 = fma(w[4 * kW], z00[j], a00);
+            a01 = fma(w[3 * kW], z00[j], a01);
+            a01 = fma(w[5 * kW], z01[j], a01);
+            a10 = fma(w[1 * kW], z00[j], a10);
+            a10 = fma(w[7 * kW], z10[j], a10);
+            a11 = fma(w[0 * kW], z00[j], a11);
+            a11 = fma(w[2 * kW], z01[j], a11);
+            a11 = fma(w[6 * kW], z10[j], a11);
+            a11 = fma(w[8 * kW], z11[j], a11);
+        }
+        out[cb + s00] = a00 * m00;
+        out[cb + s01] = a01 * m01;
+        out[cb + s10] = a10 * m10;
+        out[cb + s11] = a11 * m11;
+        m00 = n00; m01 = n01; m10 = n10; m11 = n11;
     }
 }
 
