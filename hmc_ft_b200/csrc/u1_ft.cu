@@ -273,7 +273,7 @@ constexpr int kTileStages = 3;
 // ROWS < 4 (small batches, see tile_rows_for) needs the tighter register cap: at 128 registers ptxas schedules that
 // body ~30 % slower (round-1 measurement).
 template <int LL, int ROWS, int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kConvThreads, (ROWS < 4 ? 6 : (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB)))
+__global__ void __launch_bounds__(kConvThreads, (ROWS < 4 ? 6 : (ROWS > 4 ? 3 : (EPI == EPI_BWD ? U1_TILE_BWD_MINB : U1_TILE_FWD_MINB))))
 k_conv_tile(const __grid_constant__ ConvP<CIN, COUT> p, const double* __restrict__ in,
             const double* __restrict__ add, const double* __restrict__ mul,
             double* __restrict__ out, double* __restrict__ dout, const double* __restrict__ gelu_tab) {
@@ -1418,6 +1418,12 @@ static int tile_rows_for(int nsites) {
     return ctas4 >= t4 ? 4 : (ctas4 >= t2 ? 2 : 1);
 }
 
+static bool rows8_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("U1FT_ROWS8"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 template <int CIN, int COUT, int EPI>
 static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double* in, const double* add,
                        const double* mul, double* out, double* dout, int nsites, int L, cudaStream_t st) {
@@ -1425,6 +1431,15 @@ static int launch_conv(u1ft_handle_t h, const ConvP<CIN, COUT>& p, const double*
     // against the direct kernel; the register caps of the tiled kernels are the U1_TILE_*_MINB knobs above.
     if (tile_path_enabled() && (EPI == EPI_BWD || tile_path_enabled() > 1) && (L == 32 || L == 64 || L == 128)) {
         const int rows = tile_rows_for(nsites);
+        // 12 -> 6 reverse layer (the first layer transposed): half the FMAs per channel of a 12 -> 12 layer, so 8 rows per
+        // thread (48 accumulators again; each constant-bank weight read feeds 8 DFMAs) once the launch is large enough
+        if constexpr (EPI == EPI_BWD && COUT == kXC) {
+            if (rows == 4 && rows8_enabled() && nsites / (8 * kConvThreads) >= 600) {
+                if (L == 64) return launch_conv_tile<64, 8, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+                if (L == 32) return launch_conv_tile<32, 8, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+                if (L == 128) return launch_conv_tile<128, 8, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
+            }
+        }
 #define U1_TILE_CASE(LLv, Rv) \
         if (L == LLv && rows == Rv) return launch_conv_tile<LLv, Rv, CIN, COUT, EPI>(h, p, in, add, mul, out, dout, nsites, st);
         U1_TILE_CASE(64, 4) U1_TILE_CASE(64, 2) U1_TILE_CASE(64, 1)
