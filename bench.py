@@ -368,8 +368,8 @@ def run_ours(args):
     obs_bytes = 4 * B * 8
 
     def e2e_step():
-        # public host-buffer call: sliced H2D -> trajectory kernel -> D2H pipeline over CUDA streams
-        he.step_host(theta_host, out_host, n_slices=8)
+        # public host-buffer call: sliced H2D -> trajectory kernel -> D2H pipeline, one CUDA stream per engine
+        he.step_host(theta_host, out_host)
         torch.cuda.current_stream().synchronize()                      # configurations + observables on the host
     ms_e = time_steps(e2e_step, max(3, args.steps // 2), 3, world)
     ms_copy = pinned_copy_ceiling(theta_host, out_host, dev, world)

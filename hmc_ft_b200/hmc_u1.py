@@ -139,15 +139,17 @@ class HMC_U1:
             self.traj_counter += n_traj
         return out
 
-    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices=8):
+    def step_host(self, theta_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_slices=12):
         """One Metropolis step of a HOST-resident batch [B,2,L,L] (fp64, ideally pinned): the batch is cut
-        into `n_slices` slices (or, with n_slices="tapered", ten slices of 1/32 .. 1/4 .. 1/32 of the batch)
-        whose H2D copy, trajectory kernel and D2H copy run on rotating CUDA
-        streams, so the two PCIe directions and the SMs overlap.  Returns (theta_out_host, obs_host)
-        with obs_host = pinned fp64 [4,B] = (accept, H, plaq, topo).  Chains keep their global Philox
-        ids (chain_offset + index), so the result equals the resident path bit for bit.
-        The D2H copies are ASYNCHRONOUS on the current stream: synchronize it (or the device) before the
-        host reads `theta_out_host` / `obs_host`."""
+        into `n_slices` slices (or, with n_slices="tapered", ten slices of 1/32 .. 1/4 .. 1/32 of the batch).
+        Three CUDA streams, one per engine: ALL host-to-device copies queue back to back on the first, the
+        trajectory kernels of the slices on the second (each waits for its slice's copy event), ALL
+        device-to-host copies on the third (each waits for its slice's kernel event), so neither PCIe direction
+        ever waits for the other and only the first copy-in and the last copy-out are exposed.
+        Returns (theta_out_host, obs_host) with obs_host = pinned fp64 [4,B] = (accept, H, plaq, topo).
+        Chains keep their global Philox ids (chain_offset + index), so the result equals the resident path bit
+        for bit.  The D2H copies are ASYNCHRONOUS on the current stream: synchronize it (or the device) before
+        the host reads `theta_out_host` / `obs_host`."""
         if theta_host.device.type != "cpu" or theta_host.dim() != 4 or theta_host.dtype != torch.float64:
             raise ValueError("step_host expects a CPU fp64 tensor [B,2,L,L]")
         B, L = check_field(theta_host)
@@ -175,29 +177,36 @@ class HMC_U1:
                   "obs_d": torch.empty((4, B), dtype=torch.float64, device=dev),
                   "obs_h": torch.empty((4, B), dtype=torch.float64).pin_memory(),
                   "acc": torch.empty(B, dtype=torch.int32, device=dev),
-                  "streams": [torch.cuda.Stream(device=dev) for _ in range(min(3, n_slices))]}
+                  "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],      # H2D, kernels, D2H
+                  "ev_in": [torch.cuda.Event() for _ in range(n_slices)],
+                  "ev_k": [torch.cuda.Event() for _ in range(n_slices)]}
             self._host_state = st
         cur = torch.cuda.current_stream(dev)
+        s_in, s_k, s_out = st["streams"]
         widest = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
         with torch.cuda.device(dev):
-            ws_all = [WS.get(dev, self._lib.u1_workspace_bytes(widest + 1, L), f"host{j}")
-                      for j in range(len(st["streams"]))]
+            ws, nb = WS.get(dev, self._lib.u1_workspace_bytes(widest + 1, L), "host0")
+            for s in st["streams"]:
+                s.wait_stream(cur)
+            o = st["obs_d"]
             for i in range(n_slices):
                 a, b = bounds[i], bounds[i + 1]
-                s = st["streams"][i % len(st["streams"])]
-                s.wait_stream(cur)
-                with torch.cuda.stream(s):
-                    d = st["dev"][a:b]
+                d = st["dev"][a:b]
+                with torch.cuda.stream(s_in):
                     d.copy_(theta_host[a:b], non_blocking=True)
-                    ws, nb = ws_all[i % len(st["streams"])]
-                    o = st["obs_d"]
+                    st["ev_in"][i].record(s_in)
+                with torch.cuda.stream(s_k):
+                    s_k.wait_event(st["ev_in"][i])
                     _lib.check(self._lib.u1_trajectory(
                         d.data_ptr(), None, None, self.seed, self.chain_offset + a, self.traj_counter, 1,
                         b - a, L, self.beta, self.dt, self.n_steps, None, st["acc"][a:b].data_ptr(),
                         o[1, a:b].data_ptr(), o[2, a:b].data_ptr(), o[3, a:b].data_ptr(), self.kernel_path,
-                        ws, nb, s.cuda_stream), "u1_trajectory")
+                        ws, nb, s_k.cuda_stream), "u1_trajectory")
                     self.gpu_launches += _lib.last_launch_count()
                     o[0, a:b].copy_(st["acc"][a:b])
+                    st["ev_k"][i].record(s_k)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(st["ev_k"][i])
                     out_host[a:b].copy_(d, non_blocking=True)
             for s in st["streams"]:
                 cur.wait_stream(s)

@@ -15,5 +15,5 @@ def timed(fn, reps=10):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / reps * 1e3
 for rep in range(2):
-    for ns in (4, 8, "tapered", 12, 16):
+    for ns in (8, 16, "tapered", 32, 64):
         print("n_slices", ns, f"{timed(lambda: h.step_host(th, out, n_slices=ns)):.2f} ms")
