@@ -632,7 +632,7 @@ k_drift_sums(const double* __restrict__ th, const double* __restrict__ pi, doubl
         Bv[r] = wrap_pi(fma(a, P1[r], T1[r]));
         if (r < kDsRows) {
             A[r] = wrap_pi(fma(a, P0[r], T0[r]));
-            s_a[r][tid] = A[r];
+            if (live) s_a[r][tid] = A[r];                      // (a dead thread's slot is written by its left neighbour: `edge`)
         }
     }
     if (edge) {
