@@ -223,10 +223,23 @@ class HMC_U1:
         B, L = check_field(d)
         pi_d = None if pi is None else to_dev(as_batch(pi)[0], self._dev).reshape(1, B, 2, L, L)
         u_d = None if u is None else to_dev(torch.as_tensor(u, dtype=torch.float64).reshape(-1), self._dev)
-        r = self.trajectories(d, 1, pi_d, u_d, want_obs=False)
         if single:
-            acc, H = r["accept"][0, 0].item(), r["H"][0, 0].item()      # host sync, as in the reference
-            return self._back(d, theta, True), bool(acc), H
+            # one chain (the reference's own mode, BASELINE configs[0]): latency matters, not throughput - the kernel
+            # writes H (fp64) and the accept flag (int32) into ONE 16-byte device buffer, read back with a single
+            # synchronising copy (the reference also syncs here: it returns Python scalars)
+            dev = self._dev
+            buf = torch.empty(2, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                ws, nb = self._ws(1)
+                _lib.check(self._lib.u1_trajectory(
+                    d.data_ptr(), ptr(pi_d), ptr(u_d), self.seed, self.chain_offset, self.traj_counter, 1,
+                    1, L, self.beta, self.dt, self.n_steps, None, buf.data_ptr() + 8, buf.data_ptr(), None, None,
+                    self.kernel_path, ws, nb, stream_ptr(dev)), "u1_trajectory")
+            self.gpu_launches += _lib.last_launch_count()
+            self.traj_counter += 1
+            h = buf.cpu()
+            return self._back(d, theta, True), bool(h.view(torch.int32)[2].item()), h[0].item()
+        r = self.trajectories(d, 1, pi_d, u_d, want_obs=False)
         return self._back(d, theta), self._back(r["accept"][0].bool(), theta), self._back(r["H"][0], theta)
 
     def tune_step_size(self, n_tune_steps=2000, target_rate=0.65, target_tolerance=0.15,
