@@ -63,10 +63,13 @@ def test_golden_ft(golden_dir, tag, wfile):
 
 @pytest.mark.parametrize("arch,wfile,L,B", [("rnet1", "weights_rnet1_beta6.0.npz", 16, 5),
                                              ("simple", "weights_simple_beta6.0.npz", 10, 3),
-                                             ("rnet3", "weights_rnet3_beta3.0.npz", 12, 4)])
+                                             ("rnet3", "weights_rnet3_beta3.0.npz", 12, 4),
+                                             ("simple", "weights_simple_beta6.0.npz", 96, 2),
+                                             ("rnet1", "weights_rnet1_beta6.0.npz", 128, 2)])
 def test_batched_vs_oracle_and_chunking(golden_dir, arch, wfile, L, B):
     """Batch of hot configurations (large angles -> all branches of wrap / masks), any even L,
-    and the same batch processed in chunks of 2 chains."""
+    and the same batch processed in chunks of 2 chains.  L = 96: generic convolution kernels with the fused
+    (direct-load) final layer; L = 128: the tiled kernels with one row group per CTA and the 64-wide reverse fusion."""
     from hmc_ft_b200 import _lib
     ft = make_ft(golden_dir, L, wfile)
     _, nets = O.load_weights_npz(os.path.join(golden_dir, wfile))
