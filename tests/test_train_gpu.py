@@ -78,3 +78,25 @@ def test_gradient_finite_difference(golden_dir):
     fd = (vals[0] - vals[1]) / (2 * eps)
     an = float((gradW.cpu() * flat_dir).sum().item())
     assert abs(fd - an) < 2e-5 * max(1.0, abs(an)), (fd, an)
+
+
+def test_train_loop_epochs_checkpoint_and_reload(golden_dir, tmp_path, monkeypatch):
+    """field_trans_opt.py:507-584: train() runs epochs of train_step / evaluate_step, keeps the best checkpoint in the
+    reference's file format (models/best_model_opt_L{L}_train_beta{beta}.pt, per-subset state dicts) and re-loads it at the
+    end; the re-loaded weights reproduce the best test loss."""
+    ft, z, keys = _load(golden_dir, "simple_L16")
+    monkeypatch.chdir(tmp_path)                      # the checkpoint path is CWD-relative like the reference's
+    g = torch.Generator().manual_seed(3)
+    base = torch.tensor(z["theta_ori"])
+    base = base[None] if base.dim() == 3 else base
+    data = torch.cat([base[:1] + 0.05 * torch.randn(6, *base.shape[1:], generator=g, dtype=torch.float64)])
+    train_data, test_data = data[:4], data[4:]
+    beta = float(z["train_beta"])
+    tr, te = ft.train(train_data, test_data, beta, n_epochs=3, batch_size=2)
+    assert len(tr) == 3 and len(te) == 3 and all(np.isfinite(tr)) and all(np.isfinite(te))
+    path = tmp_path / "models" / f"best_model_opt_L16_train_beta{beta:.1f}.pt"
+    assert path.exists()
+    ck = torch.load(path, weights_only=False)
+    assert {f"model_state_dict_{i}" for i in range(8)} <= set(ck) and ck["loss"] == min(te)
+    ev = float(np.mean([ft.evaluate_step(test_data[i:i + 2]) for i in range(0, 2, 2)]))
+    assert abs(ev - min(te)) < 1e-9 * abs(min(te))
